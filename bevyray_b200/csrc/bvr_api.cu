@@ -1,0 +1,587 @@
+// bvr_api.cu — the C ABI (include/bevyray_b200.h): context, scene upload, render dispatch.
+//
+// Replaces, for the hot path only, RaytracingPipeline::from_world and RayTracingNode::run of the
+// reference (src/raytracing/pipeline.rs:58-331).  There is no CPU fallback: without a CUDA device
+// bvr_create fails with BVR_ERR_NO_DEVICE.
+
+#include "../../include/bevyray_b200.h"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace bvr;
+
+namespace {
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;   // growth slack so that small scene growth does not realloc
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+struct PinnedBuffer {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) { cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&ptr, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct BvrContext {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string error;
+
+    // scene, reference layout (raw bytes in HBM) and the derived traversal layout
+    DeviceBuffer raw_models, raw_materials, raw_nodes;
+    DeviceBuffer spheres, sphere_material, pairs, inner_id, block_sums, root_ref;
+    size_t n_models = 0, n_materials = 0, n_nodes = 0;
+    bool scene_uploaded = false;
+    bool has_scene = false;
+    uint32_t root_ref_host = 0;
+    uint32_t tree_depth = 0;
+    PinnedBuffer upload_staging;
+    cudaEvent_t upload_done = nullptr;
+    bool upload_pending = false;
+
+    // per-frame IO for the host-buffer entry point
+    DeviceBuffer in_rgba, in_depth, out_rgba, out_rt_depth, out_id, out_pdepth, out_srgb8;
+    PinnedBuffer io_staging;
+
+    DeviceBuffer ray_counter;
+    unsigned long long* ray_counter_host = nullptr;   // pinned
+    cudaEvent_t ev_render0 = nullptr, ev_render1 = nullptr, ev_upload0 = nullptr, ev_upload1 = nullptr;
+    bool render_timed = false, upload_timed = false;
+    BvrStats stats{};
+};
+
+namespace {
+
+int fail(BvrContext* ctx, int status, const std::string& msg) {
+    if (ctx) ctx->error = msg;
+    return status;
+}
+
+int fail_cuda(BvrContext* ctx, cudaError_t e, const char* what) {
+    std::string msg = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    cudaGetLastError();   // clear the sticky-less error state
+    return fail(ctx, e == cudaErrorMemoryAllocation ? BVR_ERR_OUT_OF_MEMORY : BVR_ERR_CUDA, msg);
+}
+
+#define BVR_CK(expr)                                                         \
+    do {                                                                     \
+        cudaError_t e__ = (expr);                                            \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #expr);           \
+    } while (0)
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+uint32_t effective_strip_rows(const BvrRenderOptions* o) { return (o && o->strip_rows) ? o->strip_rows : 8u; }
+
+uint32_t shard_rows_impl(uint32_t height, const BvrRenderOptions* o) {
+    const uint32_t count = (o && o->shard_count > 1) ? o->shard_count : 1u;
+    if (count == 1u) return height;
+    const uint32_t r = effective_strip_rows(o);
+    const uint32_t strips = (height + r - 1) / r;
+    const uint32_t per = (strips + count - 1) / count;
+    return per * r;
+}
+
+// Host-side structural validation of the node array against the reference contract
+// (raytrace.wgsl:80-87, 313-346): everything reachable from node 0 exactly once, indices in range.
+// Also yields the tree depth (stack bound for the near-first traversal).
+int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, size_t n_materials,
+                   const BvrBvhNode* nodes, size_t n_nodes, uint32_t* depth_out) {
+    (void)models;
+    *depth_out = 0;
+    if (n_models > 0 && n_materials == 0) return fail(ctx, BVR_ERR_BAD_SCENE, "models without materials");
+    if (n_models >= (size_t)BVR_LEAF_FIRST_MASK) return fail(ctx, BVR_ERR_BAD_SCENE, "more than 2^24-1 models");
+    if (n_nodes == 0) return BVR_OK;
+    if (n_nodes >= 0x7fffffffull) return fail(ctx, BVR_ERR_BAD_SCENE, "too many BVH nodes");
+    std::vector<uint8_t> seen(n_nodes, 0);
+    std::vector<std::pair<uint32_t, uint32_t>> stack;   // (node, depth)
+    stack.push_back({0u, 1u});
+    seen[0] = 1;
+    uint32_t max_depth = 0;
+    while (!stack.empty()) {
+        const auto [i, d] = stack.back();
+        stack.pop_back();
+        if (d > max_depth) max_depth = d;
+        const BvrBvhNode& nd = nodes[i];
+        if (nd.model_count > 0) {
+            if (nd.model_count > BVR_MAX_LEAF_COUNT) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf with more than 128 models");
+            if ((size_t)nd.index + nd.model_count > n_models) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf model range out of bounds");
+        } else {
+            if ((size_t)nd.index + 1 >= n_nodes) return fail(ctx, BVR_ERR_BAD_SCENE, "child index out of bounds");
+            for (uint32_t c = nd.index; c < nd.index + 2; c++) {
+                if (seen[c]) return fail(ctx, BVR_ERR_BAD_SCENE, "BVH node referenced twice (cycle or DAG)");
+                seen[c] = 1;
+                stack.push_back({c, d + 1});
+            }
+        }
+    }
+    *depth_out = max_depth;
+    return BVR_OK;
+}
+
+// copy `bytes` from host memory to device, via pinned staging unless the source is already pinned
+int h2d(BvrContext* ctx, void* dst, const void* src, size_t bytes, PinnedBuffer& staging, size_t& staging_off) {
+    if (bytes == 0) return BVR_OK;
+    if (is_pinned_host(src)) {
+        BVR_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        char* st = static_cast<char*>(staging.ptr) + staging_off;
+        std::memcpy(st, src, bytes);
+        BVR_CK(cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        staging_off += (bytes + 255) & ~(size_t)255;
+    }
+    ctx->stats.h2d_bytes += bytes;
+    return BVR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t bvr_abi_version(void) { return BVR_ABI_VERSION; }
+
+const char* bvr_status_string(int status) {
+    switch (status) {
+        case BVR_OK: return "ok";
+        case BVR_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case BVR_ERR_CUDA: return "CUDA error";
+        case BVR_ERR_UNSUPPORTED_PROJECTION: return "unsupported projection (only perspective, projection == 0)";
+        case BVR_ERR_NO_SCENE: return "no scene uploaded";
+        case BVR_ERR_BAD_SCENE: return "malformed scene";
+        case BVR_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case BVR_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        default: return "unknown status";
+    }
+}
+
+int bvr_create(int device, BvrContext** out_ctx) {
+    if (!out_ctx) return BVR_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); return BVR_ERR_NO_DEVICE; }
+    if (device < 0 || device >= count) return BVR_ERR_INVALID_ARGUMENT;
+    BvrContext* ctx = new (std::nothrow) BvrContext();
+    if (!ctx) return BVR_ERR_OUT_OF_MEMORY;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_render0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_render1);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_upload0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_upload1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->upload_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = ctx->ray_counter.ensure(sizeof(unsigned long long));
+    if (e == cudaSuccess) e = ctx->root_ref.ensure(sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->ray_counter_host, sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        bvr_destroy(ctx);
+        return e == cudaErrorMemoryAllocation ? BVR_ERR_OUT_OF_MEMORY : BVR_ERR_CUDA;
+    }
+    *ctx->ray_counter_host = 0;
+    ctx->stream = ctx->own_stream;
+    *out_ctx = ctx;
+    return BVR_OK;
+}
+
+void bvr_destroy(BvrContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
+                            &ctx->sphere_material, &ctx->pairs, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
+                            &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter};
+    for (DeviceBuffer* b : bufs) b->release();
+    ctx->upload_staging.release();
+    ctx->io_staging.release();
+    if (ctx->ray_counter_host) cudaFreeHost(ctx->ray_counter_host);
+    cudaEvent_t evs[] = {ctx->ev_render0, ctx->ev_render1, ctx->ev_upload0, ctx->ev_upload1, ctx->upload_done};
+    for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+const char* bvr_last_error(const BvrContext* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int bvr_set_stream(BvrContext* ctx, void* cuda_stream) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    BVR_CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return BVR_OK;
+}
+
+int bvr_sync(BvrContext* ctx) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    BVR_CK(cudaStreamSynchronize(ctx->stream));
+    return BVR_OK;
+}
+
+int bvr_upload_scene(BvrContext* ctx,
+                     const BvrModel* models, size_t n_models,
+                     const BvrMaterial* materials, size_t n_materials,
+                     const BvrBvhNode* nodes, size_t n_nodes,
+                     const BvrDirtyRange* ranges, size_t n_ranges) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    if ((n_models && !models) || (n_materials && !materials) || (n_nodes && !nodes))
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null array with non-zero count");
+    if (n_ranges && !ranges) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null ranges with non-zero count");
+    cudaSetDevice(ctx->device);
+
+    const bool partial = ranges != nullptr && ctx->scene_uploaded && n_models == ctx->n_models &&
+                         n_materials == ctx->n_materials && n_nodes == ctx->n_nodes;
+    if (ranges && !partial && ctx->scene_uploaded)
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty ranges given but the element counts changed");
+    if (ranges && !ctx->scene_uploaded)
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty ranges given before any full upload");
+
+    uint32_t depth = 0;
+    int st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth);
+    if (st != BVR_OK) return st;
+
+    // the ranges to copy
+    struct Copy { uint32_t array; size_t first, count; };
+    std::vector<Copy> copies;
+    const size_t counts[3] = {n_models, n_materials, n_nodes};
+    const size_t strides[3] = {sizeof(BvrModel), sizeof(BvrMaterial), sizeof(BvrBvhNode)};
+    if (partial) {
+        for (size_t i = 0; i < n_ranges; i++) {
+            const BvrDirtyRange& r = ranges[i];
+            if (r.array > 2u) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty range: bad array id");
+            if ((size_t)r.first + r.count > counts[r.array])
+                return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty range out of bounds");
+            if (r.count) copies.push_back({r.array, r.first, r.count});
+        }
+    } else {
+        for (uint32_t a = 0; a < 3; a++) if (counts[a]) copies.push_back({a, 0, counts[a]});
+    }
+
+    BVR_CK(ctx->raw_models.ensure(n_models * sizeof(BvrModel)));
+    BVR_CK(ctx->raw_materials.ensure(n_materials * sizeof(BvrMaterial)));
+    BVR_CK(ctx->raw_nodes.ensure(n_nodes * sizeof(BvrBvhNode)));
+    BVR_CK(ctx->spheres.ensure(n_models * sizeof(float4)));
+    BVR_CK(ctx->sphere_material.ensure(n_models * sizeof(uint32_t)));
+    BVR_CK(ctx->pairs.ensure(n_nodes * 2 * sizeof(float4)));   // <= ceil(n/2) inner nodes x 64 B
+    BVR_CK(ctx->inner_id.ensure(n_nodes * sizeof(uint32_t)));
+    BVR_CK(ctx->block_sums.ensure((n_nodes / 1024 + 2) * sizeof(uint32_t)));
+
+    // stage + copy
+    size_t staging_bytes = 0;
+    for (const Copy& c : copies) staging_bytes += ((c.count * strides[c.array]) + 255) & ~(size_t)255;
+    if (ctx->upload_pending) { BVR_CK(cudaEventSynchronize(ctx->upload_done)); ctx->upload_pending = false; }
+    BVR_CK(ctx->upload_staging.ensure(staging_bytes));
+    BVR_CK(cudaEventRecord(ctx->ev_upload0, ctx->stream));
+    const void* src_base[3] = {models, materials, nodes};
+    void* dst_base[3] = {ctx->raw_models.ptr, ctx->raw_materials.ptr, ctx->raw_nodes.ptr};
+    size_t off = 0;
+    bool models_dirty = false, nodes_dirty = false;
+    for (const Copy& c : copies) {
+        const size_t stride = strides[c.array];
+        st = h2d(ctx, static_cast<char*>(dst_base[c.array]) + c.first * stride,
+                 static_cast<const char*>(src_base[c.array]) + c.first * stride, c.count * stride,
+                 ctx->upload_staging, off);
+        if (st != BVR_OK) return st;
+        if (c.array == BVR_ARRAY_MODELS) models_dirty = true;
+        if (c.array == BVR_ARRAY_BVH_NODES) nodes_dirty = true;
+    }
+    BVR_CK(cudaEventRecord(ctx->upload_done, ctx->stream));
+    ctx->upload_pending = true;
+
+    // derive the traversal layout in HBM
+    int launches = 0;
+    if (models_dirty || !partial)
+        launches += launch_derive_spheres(ctx->raw_models.as<RawModel>(), (uint32_t)n_models,
+                                          ctx->spheres.as<float4>(), ctx->sphere_material.as<uint32_t>(), ctx->stream);
+    if (nodes_dirty || !partial) {
+        launches += launch_derive_pairs(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+                                        ctx->block_sums.as<uint32_t>(), ctx->pairs.as<float4>(),
+                                        ctx->root_ref.as<uint32_t>(), ctx->stream);
+        // root ref on the host (needed as a kernel parameter): a leaf root is encoded like any leaf ref
+        if (n_nodes) {
+            const BvrBvhNode& r = nodes[0];
+            ctx->root_ref_host = r.model_count > 0
+                                     ? (BVR_LEAF_BIT | ((r.model_count - 1u) << 24) | (r.index & BVR_LEAF_FIRST_MASK))
+                                     : 0u;   // node 0 is the first inner node -> dense id 0
+        }
+    }
+    BVR_CK(cudaGetLastError());
+    BVR_CK(cudaEventRecord(ctx->ev_upload1, ctx->stream));
+    ctx->upload_timed = true;
+    ctx->stats.kernel_launches += (uint64_t)launches;
+    ctx->n_models = n_models;
+    ctx->n_materials = n_materials;
+    ctx->n_nodes = n_nodes;
+    ctx->tree_depth = depth;
+    ctx->has_scene = n_nodes > 0 && n_models > 0;
+    ctx->scene_uploaded = true;
+    return BVR_OK;
+}
+
+uint32_t bvr_shard_rows(uint32_t height, const BvrRenderOptions* opts) { return shard_rows_impl(height, opts); }
+
+static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level,
+                        const BvrWindow* window, const BvrRenderOptions* opts, RenderParams* out) {
+    if (!camera || !level || !window || !opts) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null uniform / options pointer");
+    if (!ctx->scene_uploaded) return fail(ctx, BVR_ERR_NO_SCENE, "bvr_render before bvr_upload_scene");
+    if (camera->projection != 0u) return fail(ctx, BVR_ERR_UNSUPPORTED_PROJECTION, "camera.projection != 0");
+    if (opts->width == 0 || window->height == 0) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "zero image size");
+    if (level->level > 3u) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "raytrace level > 3");
+    if (opts->shard_count > 1 && opts->shard_index >= opts->shard_count)
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "shard_index >= shard_count");
+    if (opts->kernel > BVR_KERNEL_WAVEFRONT || opts->traversal > BVR_TRAVERSAL_REFERENCE_ORDER)
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "unknown kernel / traversal");
+
+    RenderParams p;
+    std::memset(&p, 0, sizeof p);
+    p.scene.pairs = ctx->pairs.as<float4>();
+    p.scene.spheres = ctx->spheres.as<float4>();
+    p.scene.sphere_material = ctx->sphere_material.as<uint32_t>();
+    p.scene.materials = ctx->raw_materials.as<float4>();
+    p.scene.root_ref = ctx->root_ref_host;
+    p.scene.n_materials = (uint32_t)ctx->n_materials;
+    p.scene.has_scene = ctx->has_scene ? 1u : 0u;
+
+    CameraParams& c = p.cam;
+    c.position = V3{camera->position[0], camera->position[1], camera->position[2]};
+    c.direction = V3{camera->direction[0], camera->direction[1], camera->direction[2]};
+    c.up = V3{camera->up[0], camera->up[1], camera->up[2]};
+    // cross(direction, up), raytrace.wgsl:149 — plain f32 mul/sub, compiled without FMA contraction
+    {
+        const volatile float dx = c.direction.x, dy = c.direction.y, dz = c.direction.z;
+        const volatile float ux = c.up.x, uy = c.up.y, uz = c.up.z;
+        const volatile float a0 = dy * uz, a1 = dz * uy, b0 = dz * ux, b1 = dx * uz, c0 = dx * uy, c1 = dy * ux;
+        c.right = V3{a0 - a1, b0 - b1, c0 - c1};
+    }
+    c.aspect = camera->aspect;
+    c.tan_half_fov = (float)std::tan((double)(camera->fov * 0.5f));       // raytrace.wgsl:151
+    {
+        const volatile float h = (float)window->height;
+        const volatile float w = h * camera->aspect;                          // raytrace.wgsl:142
+        c.inv_width = 1.0f / w;
+        c.inv_height = 1.0f / h;
+    }
+    c.near_plane = camera->near_plane;
+    c.far_plane = camera->far_plane;
+    c.fallback_far = (level->level == 1u) ? camera->far_plane + 10.0f : camera->far_plane - 1.0f;
+    c.seed_scaled = window->random_seed * 10000.0f;
+    c.sample_count = camera->sample_count;
+    c.bounce_count = camera->bounce_count;
+    c.level = level->level;
+    c.width = opts->width;
+    c.height = window->height;
+
+    p.shard.count = opts->shard_count > 1 ? opts->shard_count : 1u;
+    p.shard.index = opts->shard_count > 1 ? opts->shard_index : 0u;
+    p.shard.strip_rows = p.shard.count > 1 ? effective_strip_rows(opts) : window->height;
+    p.shard.rows = shard_rows_impl(window->height, opts);
+    p.ray_counter = ctx->ray_counter.as<unsigned long long>();
+    // the near-first stack holds one entry per level; deeper trees use the reference-order traversal
+    p.reference_order = (opts->traversal == BVR_TRAVERSAL_REFERENCE_ORDER || ctx->tree_depth + 1 > BVR_FAST_STACK) ? 1u : 0u;
+    *out = p;
+    return BVR_OK;
+}
+
+static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level,
+                              const BvrWindow* window, const BvrRenderOptions* opts,
+                              const float* d_raster_rgba, const float* d_raster_depth, const BvrOutputs* out) {
+    RenderParams p;
+    int st = build_params(ctx, camera, level, window, opts, &p);
+    if (st != BVR_OK) return st;
+    if (!out) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null outputs");
+    if (p.cam.level <= 2u && !d_raster_rgba) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "levels 0-2 need the raster colour");
+    if ((p.cam.level == 1u || p.cam.level == 2u) && !d_raster_depth)
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "levels 1-2 need the raster depth");
+    p.raster_rgba = reinterpret_cast<const float4*>(d_raster_rgba);
+    p.raster_depth = d_raster_depth;
+    p.out_rgba = reinterpret_cast<float4*>(out->rgba);
+    p.out_rt_depth = out->rt_depth;
+    p.out_primary_id = out->primary_id;
+    p.out_primary_depth = out->primary_depth;
+    p.out_srgb8 = reinterpret_cast<uchar4*>(out->srgb8);
+
+    BVR_CK(cudaMemsetAsync(ctx->ray_counter.ptr, 0, sizeof(unsigned long long), ctx->stream));
+    BVR_CK(cudaEventRecord(ctx->ev_render0, ctx->stream));
+    int launches = 0;
+    if (p.cam.level == 0u) {
+        launches += launch_copy_raster(p, ctx->stream);
+    } else {
+        launches += launch_megakernel(p, ctx->stream);
+    }
+    BVR_CK(cudaGetLastError());
+    BVR_CK(cudaEventRecord(ctx->ev_render1, ctx->stream));
+    BVR_CK(cudaMemcpyAsync(ctx->ray_counter_host, ctx->ray_counter.ptr, sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->render_timed = true;
+    ctx->stats.kernel_launches += (uint64_t)launches;
+    // paths = pixels of this shard that exist x samples
+    uint64_t rows = 0;
+    for (uint32_t ly = 0; ly < p.shard.rows; ly++) if (shard_global_row(p.shard, ly) < p.cam.height) rows++;
+    ctx->stats.paths = p.cam.level == 0u ? 0u : rows * (uint64_t)p.cam.width * p.cam.sample_count;
+    return BVR_OK;
+}
+
+int bvr_render_device(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level,
+                      const BvrWindow* window, const BvrRenderOptions* opts,
+                      const float* d_raster_rgba, const float* d_raster_depth, const BvrOutputs* device_out) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    cudaSetDevice(ctx->device);
+    return render_device_impl(ctx, camera, level, window, opts, d_raster_rgba, d_raster_depth, device_out);
+}
+
+int bvr_render(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level, const BvrWindow* window,
+               const BvrRenderOptions* opts, const float* raster_rgba, const float* raster_depth,
+               const BvrOutputs* host_out) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    if (!camera || !level || !window || !opts || !host_out)
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null uniform / options / outputs pointer");
+    cudaSetDevice(ctx->device);
+    const size_t full_px = (size_t)opts->width * window->height;
+    const size_t shard_px = (size_t)opts->width * shard_rows_impl(window->height, opts);
+    const bool need_rgba = level->level <= 2u, need_depth = level->level == 1u || level->level == 2u;
+    if (need_rgba && !raster_rgba) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "levels 0-2 need the raster colour");
+    if (need_depth && !raster_depth) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "levels 1-2 need the raster depth");
+
+    // inputs: pinned (or staged) host -> HBM
+    size_t in_staging = 0;
+    if (need_rgba && !is_pinned_host(raster_rgba)) in_staging += (full_px * 16 + 255) & ~(size_t)255;
+    if (need_depth && !is_pinned_host(raster_depth)) in_staging += (full_px * 4 + 255) & ~(size_t)255;
+    // outputs: HBM -> pinned (or staged) host
+    struct Plane { void* host; DeviceBuffer* dev; size_t bytes; bool pinned; size_t off; };
+    Plane planes[5] = {
+        {host_out->rgba, &ctx->out_rgba, shard_px * 16, false, 0},
+        {host_out->rt_depth, &ctx->out_rt_depth, shard_px * 4, false, 0},
+        {host_out->primary_id, &ctx->out_id, shard_px * 4, false, 0},
+        {host_out->primary_depth, &ctx->out_pdepth, shard_px * 4, false, 0},
+        {host_out->srgb8, &ctx->out_srgb8, shard_px * 4, false, 0},
+    };
+    size_t out_staging = 0;
+    for (Plane& pl : planes) {
+        if (!pl.host) continue;
+        pl.pinned = is_pinned_host(pl.host);
+        if (!pl.pinned) { pl.off = out_staging; out_staging += (pl.bytes + 255) & ~(size_t)255; }
+        BVR_CK(pl.dev->ensure(pl.bytes));
+    }
+    BVR_CK(cudaStreamSynchronize(ctx->stream));   // staging reuse
+    BVR_CK(ctx->io_staging.ensure(in_staging > out_staging ? in_staging : out_staging));
+
+    size_t off = 0;
+    int st;
+    if (need_rgba) {
+        BVR_CK(ctx->in_rgba.ensure(full_px * 16));
+        if ((st = h2d(ctx, ctx->in_rgba.ptr, raster_rgba, full_px * 16, ctx->io_staging, off)) != BVR_OK) return st;
+    }
+    if (need_depth) {
+        BVR_CK(ctx->in_depth.ensure(full_px * 4));
+        if ((st = h2d(ctx, ctx->in_depth.ptr, raster_depth, full_px * 4, ctx->io_staging, off)) != BVR_OK) return st;
+    }
+
+    BvrOutputs dev_out;
+    dev_out.rgba = host_out->rgba ? ctx->out_rgba.as<float>() : nullptr;
+    dev_out.rt_depth = host_out->rt_depth ? ctx->out_rt_depth.as<float>() : nullptr;
+    dev_out.primary_id = host_out->primary_id ? ctx->out_id.as<uint32_t>() : nullptr;
+    dev_out.primary_depth = host_out->primary_depth ? ctx->out_pdepth.as<float>() : nullptr;
+    dev_out.srgb8 = host_out->srgb8 ? ctx->out_srgb8.as<uint8_t>() : nullptr;
+    st = render_device_impl(ctx, camera, level, window, opts, need_rgba ? ctx->in_rgba.as<float>() : nullptr,
+                            need_depth ? ctx->in_depth.as<float>() : nullptr, &dev_out);
+    if (st != BVR_OK) return st;
+
+    bool staged = false;
+    if (in_staging && out_staging) BVR_CK(cudaStreamSynchronize(ctx->stream));   // inputs consumed before reuse
+    for (Plane& pl : planes) {
+        if (!pl.host) continue;
+        void* dst = pl.pinned ? pl.host : static_cast<char*>(ctx->io_staging.ptr) + pl.off;
+        BVR_CK(cudaMemcpyAsync(dst, pl.dev->ptr, pl.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += pl.bytes;
+        staged |= !pl.pinned;
+    }
+    BVR_CK(cudaStreamSynchronize(ctx->stream));
+    if (staged)
+        for (Plane& pl : planes)
+            if (pl.host && !pl.pinned) std::memcpy(pl.host, static_cast<char*>(ctx->io_staging.ptr) + pl.off, pl.bytes);
+    return BVR_OK;
+}
+
+int bvr_axpby_device(BvrContext* ctx, float* d_dst, float dst_weight, const float* d_src, float src_weight, size_t n) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    if (n && (!d_dst || !d_src)) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null device pointer");
+    cudaSetDevice(ctx->device);
+    ctx->stats.kernel_launches += (uint64_t)launch_axpby(d_dst, dst_weight, d_src, src_weight, n, ctx->stream);
+    BVR_CK(cudaGetLastError());
+    return BVR_OK;
+}
+
+int bvr_unshard_device(BvrContext* ctx, const void* d_gathered, size_t shard_stride_words, void* d_full,
+                       uint32_t width, uint32_t height, uint32_t channels, uint32_t shard_count, uint32_t strip_rows) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    if (!d_gathered || !d_full || shard_count == 0 || channels == 0)
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "bad unshard arguments");
+    cudaSetDevice(ctx->device);
+    if (strip_rows == 0) strip_rows = 8;
+    if (shard_count == 1) strip_rows = height ? height : 1;
+    ctx->stats.kernel_launches += (uint64_t)launch_unshard(static_cast<const uint32_t*>(d_gathered), shard_stride_words,
+                                                           static_cast<uint32_t*>(d_full), width, height, channels,
+                                                           shard_count, strip_rows, ctx->stream);
+    BVR_CK(cudaGetLastError());
+    return BVR_OK;
+}
+
+int bvr_get_stats(BvrContext* ctx, BvrStats* out) {
+    if (!ctx || !out) return BVR_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    BVR_CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->render_timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev_render0, ctx->ev_render1) == cudaSuccess) ctx->stats.last_render_ms = ms;
+        else cudaGetLastError();
+        ctx->stats.rays = *ctx->ray_counter_host;
+    }
+    if (ctx->upload_timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev_upload0, ctx->ev_upload1) == cudaSuccess) ctx->stats.last_upload_ms = ms;
+        else cudaGetLastError();
+    }
+    *out = ctx->stats;
+    return BVR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// kernels.cuh — launch-side declarations shared between bvr_api.cu and the kernel translation units.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "trace.cuh"
+
+namespace bvr {
+
+struct ShardParams {
+    uint32_t index, count, strip_rows;
+    uint32_t rows;   // rows of this shard's planes (padded to whole strips, equal on every shard)
+};
+
+struct RenderParams {
+    SceneView scene;
+    CameraParams cam;
+    ShardParams shard;
+    // inputs (full image), may be null for level 3
+    const float4* raster_rgba;
+    const float* raster_depth;
+    // outputs (shard-local planes), any may be null
+    float4* out_rgba;
+    float* out_rt_depth;
+    uint32_t* out_primary_id;
+    float* out_primary_depth;
+    uchar4* out_srgb8;
+    unsigned long long* ray_counter;   // += raycast() invocations
+    uint32_t reference_order;          // BvrTraversal
+};
+
+// global row of shard-local row `ly`; >= height for padding rows
+__host__ __device__ __forceinline__ uint32_t shard_global_row(const ShardParams& s, uint32_t ly) {
+    const uint32_t strip = ly / s.strip_rows;
+    return (strip * s.count + s.index) * s.strip_rows + (ly % s.strip_rows);
+}
+
+// ---- scene derivation (scene_kernels.cu) ----
+struct RawNode {   // BvrBvhNode bytes
+    float mn[3]; uint32_t pad0; float mx[3]; uint32_t index; uint32_t model_count; uint32_t pad1[3];
+};
+struct RawModel {  // BvrModel bytes
+    float position[3]; float radius; uint32_t material_id; uint32_t pad[3];
+};
+
+// launches; each returns the number of kernels it launched
+int launch_derive_spheres(const RawModel* models, uint32_t n, float4* spheres, uint32_t* sphere_material,
+                          cudaStream_t stream);
+// inner_id: scratch of n_nodes u32; block_sums: scratch of ceil(n_nodes/1024)+1 u32
+int launch_derive_pairs(const RawNode* nodes, uint32_t n_nodes, uint32_t* inner_id, uint32_t* block_sums,
+                        float4* pairs, uint32_t* root_ref_out, cudaStream_t stream);
+
+// ---- render kernels ----
+int launch_megakernel(const RenderParams& p, cudaStream_t stream);
+int launch_copy_raster(const RenderParams& p, cudaStream_t stream);   // level 0: raytrace.wgsl:97-99
+
+// ---- multi-GPU helpers (shard_kernels.cu) ----
+int launch_axpby(float* dst, float dst_weight, const float* src, float src_weight, size_t n, cudaStream_t stream);
+int launch_unshard(const uint32_t* gathered, size_t shard_stride_words, uint32_t* full, uint32_t width,
+                   uint32_t height, uint32_t channels, uint32_t shard_count, uint32_t strip_rows,
+                   cudaStream_t stream);
+
+}  // namespace bvr

@@ -1,0 +1,135 @@
+// scene_kernels.cu — device-side re-layout of the reference's storage buffers into the traversal
+// layout (trace.cuh).  The library accepts the reference bytes unchanged (Model 32 B, BVHNode 48 B,
+// src/raytracing/extract.rs:213-237); everything below happens in HBM after the upload.
+
+#include "kernels.cuh"
+
+namespace bvr {
+
+namespace {
+
+constexpr int SCAN_BLOCK = 1024;
+
+__global__ void derive_spheres_kernel(const RawModel* __restrict__ models, uint32_t n,
+                                      float4* __restrict__ spheres, uint32_t* __restrict__ sphere_material) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // one 32-byte model = two 16-byte loads
+    const float4 a = reinterpret_cast<const float4*>(models)[2u * i];
+    const uint4 b = reinterpret_cast<const uint4*>(models)[2u * i + 1u];
+    spheres[i] = a;                 // (position.xyz, radius)
+    sphere_material[i] = b.x;       // material_id
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& block_total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31u) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < (blockDim.x >> 5)) ? warp_sums[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= (uint32_t)o) w += y;
+        }
+        warp_sums[lane] = w;   // inclusive
+    }
+    __syncthreads();
+    const uint32_t warp_off = warp ? warp_sums[warp - 1] : 0u;
+    block_total = warp_sums[(blockDim.x >> 5) - 1];
+    return warp_off + x - v;
+}
+
+// pass 1: number of inner nodes per block of 1024
+__global__ void count_inner_kernel(const RawNode* __restrict__ nodes, uint32_t n, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t flag = (i < n && nodes[i].model_count == 0u) ? 1u : 0u;
+    uint32_t total;
+    (void)block_exclusive_scan(flag, warp_sums, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// pass 2: exclusive scan of the block sums (one block, serial over chunks)
+__global__ void scan_block_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t n_blocks) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += SCAN_BLOCK) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, warp_sums, total);
+        const uint32_t c = carry;
+        if (i < n_blocks) block_sums[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[n_blocks] = carry;   // total number of inner nodes
+}
+
+// pass 3: dense id of every inner node
+__global__ void assign_inner_id_kernel(const RawNode* __restrict__ nodes, uint32_t n,
+                                       const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ inner_id) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t flag = (i < n && nodes[i].model_count == 0u) ? 1u : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(flag, warp_sums, total);
+    if (i < n) inner_id[i] = flag ? block_sums[blockIdx.x] + ex : 0xffffffffu;
+}
+
+__device__ __forceinline__ uint32_t make_ref(const RawNode& child, uint32_t child_inner_id) {
+    if (child.model_count > 0u)
+        return BVR_LEAF_BIT | ((child.model_count - 1u) << 24) | (child.index & BVR_LEAF_FIRST_MASK);
+    return child_inner_id;
+}
+
+// pass 4: one 64-byte child-pair record per inner node
+__global__ void build_pairs_kernel(const RawNode* __restrict__ nodes, uint32_t n,
+                                   const uint32_t* __restrict__ inner_id, float4* __restrict__ pairs,
+                                   uint32_t* __restrict__ root_ref_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RawNode nd = nodes[i];
+    if (i == 0u) *root_ref_out = make_ref(nd, nd.model_count == 0u ? inner_id[0] : 0u);
+    if (nd.model_count != 0u) return;
+    const uint32_t c0i = nd.index, c1i = nd.index + 1u;
+    const RawNode c0 = nodes[c0i], c1 = nodes[c1i];
+    const uint32_t r0 = make_ref(c0, inner_id[c0i]), r1 = make_ref(c1, inner_id[c1i]);
+    float4* out = pairs + 4u * inner_id[i];
+    out[0] = make_float4(c0.mn[0], c0.mn[1], c0.mn[2], c0.mx[0]);
+    out[1] = make_float4(c0.mx[1], c0.mx[2], c1.mn[0], c1.mn[1]);
+    out[2] = make_float4(c1.mn[2], c1.mx[0], c1.mx[1], c1.mx[2]);
+    out[3] = make_float4(__uint_as_float(r0), __uint_as_float(r1), 0.0f, 0.0f);
+}
+
+}  // namespace
+
+int launch_derive_spheres(const RawModel* models, uint32_t n, float4* spheres, uint32_t* sphere_material,
+                          cudaStream_t stream) {
+    if (n == 0) return 0;
+    derive_spheres_kernel<<<(n + 255) / 256, 256, 0, stream>>>(models, n, spheres, sphere_material);
+    return 1;
+}
+
+int launch_derive_pairs(const RawNode* nodes, uint32_t n_nodes, uint32_t* inner_id, uint32_t* block_sums,
+                        float4* pairs, uint32_t* root_ref_out, cudaStream_t stream) {
+    if (n_nodes == 0) return 0;
+    const uint32_t n_blocks = (n_nodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    count_inner_kernel<<<n_blocks, SCAN_BLOCK, 0, stream>>>(nodes, n_nodes, block_sums);
+    scan_block_sums_kernel<<<1, SCAN_BLOCK, 0, stream>>>(block_sums, n_blocks);
+    assign_inner_id_kernel<<<n_blocks, SCAN_BLOCK, 0, stream>>>(nodes, n_nodes, block_sums, inner_id);
+    build_pairs_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(nodes, n_nodes, inner_id, pairs, root_ref_out);
+    return 4;
+}
+
+}  // namespace bvr

@@ -1,0 +1,55 @@
+// shard_kernels.cu — the two device helpers the multi-GPU paths need around NCCL:
+// de-interleaving gathered tile shards, and weighting per-seed partial averages.
+
+#include "kernels.cuh"
+
+namespace bvr {
+
+namespace {
+
+__global__ void axpby_kernel(float* __restrict__ dst, float dw, const float* __restrict__ src, float sw, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = __fadd_rn(__fmul_rn(dst[i], dw), __fmul_rn(src[i], sw));
+}
+
+// gathered: shard_count planes, each `shard_stride_words` words, shard-local rows of width*channels words
+__global__ void unshard_kernel(const uint32_t* __restrict__ gathered, size_t shard_stride_words,
+                               uint32_t* __restrict__ full, uint32_t width, uint32_t height, uint32_t channels,
+                               uint32_t shard_count, uint32_t strip_rows) {
+    const size_t row_words = (size_t)width * channels;
+    const size_t total = row_words * height;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t gy = (uint32_t)(i / row_words);
+        const size_t within = i - (size_t)gy * row_words;
+        const uint32_t strip = gy / strip_rows;
+        const uint32_t shard = strip % shard_count;
+        const uint32_t ly = (strip / shard_count) * strip_rows + (gy % strip_rows);
+        full[i] = gathered[(size_t)shard * shard_stride_words + (size_t)ly * row_words + within];
+    }
+}
+
+}  // namespace
+
+int launch_axpby(float* dst, float dw, const float* src, float sw, size_t n, cudaStream_t stream) {
+    if (n == 0) return 0;
+    const int block = 256;
+    const int grid = (int)((n + block - 1) / block < 148 * 8 ? (n + block - 1) / block : 148 * 8);
+    axpby_kernel<<<grid, block, 0, stream>>>(dst, dw, src, sw, n);
+    return 1;
+}
+
+int launch_unshard(const uint32_t* gathered, size_t shard_stride_words, uint32_t* full, uint32_t width,
+                   uint32_t height, uint32_t channels, uint32_t shard_count, uint32_t strip_rows,
+                   cudaStream_t stream) {
+    const size_t total = (size_t)width * height * channels;
+    if (total == 0) return 0;
+    const int block = 256;
+    const int grid = (int)((total + block - 1) / block < 148 * 8 ? (total + block - 1) / block : 148 * 8);
+    unshard_kernel<<<grid, block, 0, stream>>>(gathered, shard_stride_words, full, width, height, channels,
+                                               shard_count, strip_rows);
+    return 1;
+}
+
+}  // namespace bvr

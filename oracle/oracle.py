@@ -1,0 +1,99 @@
+"""ctypes wrapper of the CPU oracle (oracle/libbvr_oracle.so).  TEST INFRASTRUCTURE ONLY: imported by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs — never by
+bevyray_b200/."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libbvr_oracle.so")
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+if not os.path.exists(_LIB):
+    build()
+lib = C.CDLL(_LIB)
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays", "paths", "node_pops", "inner_visits", "box_tests", "sphere_tests",
+                                          "hits_shaded", "rng_draws", "stack_truncations", "max_stack")]
+
+
+_vp = C.c_void_p
+lib.bvro_rng_next_int.restype = C.c_uint32
+lib.bvro_rng_next_int.argtypes = [C.c_uint32]
+lib.bvro_rng_float_of_state.restype = C.c_float
+lib.bvro_rng_float_of_state.argtypes = [C.c_uint32]
+lib.bvro_pixel_seed.restype = C.c_uint32
+lib.bvro_pixel_seed.argtypes = [C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+lib.bvro_tan_half_fov.restype = C.c_float
+lib.bvro_tan_half_fov.argtypes = [C.c_float]
+lib.bvro_hit_sphere.restype = C.c_float
+lib.bvro_hit_sphere.argtypes = [_vp, _vp, _vp]
+lib.bvro_ray_bounding_dst.restype = C.c_float
+lib.bvro_ray_bounding_dst.argtypes = [_vp, _vp, _vp, _vp]
+lib.bvro_render.restype = C.c_int
+lib.bvro_render.argtypes = [_vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp, _vp,
+                            C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp,
+                            C.c_int, C.c_int, C.POINTER(Counters)]
+lib.bvro_store_srgb8.restype = None
+lib.bvro_store_srgb8.argtypes = [_vp, C.c_size_t, _vp]
+lib.bvro_max_threads.restype = C.c_int
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def rng_sequence(state, n):
+    out = []
+    for _ in range(n):
+        state = lib.bvro_rng_next_int(state)
+        out.append(state)
+    return out
+
+
+def render(models, materials, nodes, camera, level, window, width, raster_rgba=None, raster_depth=None,
+           rows=None, brute_force=False, threads=0):
+    """One `fragment` invocation per pixel.  camera/level/window are the ctypes structs of the C ABI
+    (any object exposing the same bytes).  Returns (planes dict, counters dict); planes are full-image."""
+    height = window.height
+    y0, y1 = (0, height) if rows is None else rows
+    rgba = np.zeros((height, width, 4), np.float32)
+    rt_depth = np.zeros((height, width), np.float32)
+    pid = np.full((height, width), 0xFFFFFFFF, np.uint32)
+    pdepth = np.zeros((height, width), np.float32)
+    models = np.ascontiguousarray(models)
+    materials = np.ascontiguousarray(materials)
+    nodes = np.ascontiguousarray(nodes)
+    if raster_rgba is not None:
+        raster_rgba = np.ascontiguousarray(raster_rgba, np.float32)
+    if raster_depth is not None:
+        raster_depth = np.ascontiguousarray(raster_depth, np.float32)
+    cnt = Counters()
+    lvl = level
+    rc = lib.bvro_render(_ptr(models), len(models), _ptr(materials), len(materials), _ptr(nodes), len(nodes),
+                         C.addressof(camera), C.addressof(lvl), C.addressof(window), width, y0, y1,
+                         _ptr(raster_rgba), _ptr(raster_depth), _ptr(rgba), _ptr(rt_depth), _ptr(pid), _ptr(pdepth),
+                         1 if brute_force else 0, threads, C.byref(cnt))
+    if rc != 0:
+        raise RuntimeError(f"bvro_render failed with status {rc}")
+    planes = {"rgba": rgba, "rt_depth": rt_depth, "primary_id": pid, "primary_depth": pdepth}
+    return planes, {k: getattr(cnt, k) for k, _ in cnt._fields_}
+
+
+def store_srgb8(rgba):
+    rgba = np.ascontiguousarray(rgba, np.float32)
+    out = np.empty(rgba.shape, np.uint8)
+    lib.bvro_store_srgb8(_ptr(rgba), rgba.size // 4, _ptr(out))
+    return out
+
+
+def max_threads():
+    return lib.bvro_max_threads()

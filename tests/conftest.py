@@ -1,0 +1,36 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def bvr():
+    import bevyray_b200
+    return bevyray_b200
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as o
+    return o
+
+
+@pytest.fixture(scope="session")
+def rtiow(bvr):
+    return bvr.Scene.rtiow(1)
+
+
+@pytest.fixture(scope="session")
+def ctx(bvr):
+    c = bvr.Context(0)
+    yield c
+    c.close()
