@@ -113,6 +113,7 @@ SIGNATURES = {
     "bvr_axpby_device": (_i, [_vp, _vp, _f, _vp, _f, _sz]),
     "bvr_unshard_device": (_i, [_vp, _vp, _sz, _vp, _u32, _u32, _u32, _u32, _u32]),
     "bvr_get_stats": (_i, [_vp, _P(BvrStats)]),
+    "bvr_bench_fp32_peak": (_i, [_i, _P(_f)]),
     # include/bevyray_b200_host.h
     "bvrh_scene_rtiow": (_vp, [_u64]),
     "bvrh_scene_random": (_vp, [_u64, _u32, _f, _f, _f]),

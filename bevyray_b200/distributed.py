@@ -1,0 +1,79 @@
+"""Multi-GPU frame rendering: one process per GPU, torch.distributed (NCCL) for the exchange step.
+
+Two shardings:
+  * "tiles"   — interleaved row strips; every rank renders its strips for all samples with the
+                reference's per-pixel RNG stream, so the gathered image is bit-identical to 1 GPU.
+                Exchange: all_gather of equal-size shard planes + one de-interleave kernel.
+  * "samples" — rank g renders `sample_count` samples of the whole frame with its own random_seed
+                (what the reference does across frames, extract.rs:72-73); the per-rank averages are
+                summed with an NCCL reduce to rank 0 and scaled by 1/world.
+torch is plumbing only (device memory, streams, NCCL); every kernel on the render path is in
+libbevyray_b200.so."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi as capi
+from .api import Context, make_level, make_options, make_window
+
+
+class ShardedRenderer:
+    def __init__(self, device, rank=0, world=1, mode="samples", strip_rows=4):
+        assert mode in ("tiles", "samples")
+        self.rank, self.world, self.mode, self.strip_rows = rank, world, mode, strip_rows
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.ctx = Context(device)
+        # a dedicated torch stream made current: the library, NCCL and torch.cuda.Event then share one
+        # stream (torch's default stream has handle 0, which bvr_set_stream reads as "own stream")
+        self.stream = torch.cuda.Stream(self.device)
+        torch.cuda.set_stream(self.stream)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        self._bufs = {}
+
+    def upload_scene(self, models, materials, nodes, ranges=None):
+        self.ctx.upload_scene(models, materials, nodes, ranges)
+
+    def seed_for_rank(self, base_seed):
+        """Distinct, deterministic random_seed in [0,1) per rank for sample sharding."""
+        if self.mode != "samples" or self.world == 1:
+            return float(np.float32(base_seed))
+        return float(np.float32((base_seed + 0.61803398875 * self.rank) % 1.0))
+
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        if key not in self._bufs:
+            self._bufs[key] = torch.empty(shape, dtype=dtype, device=self.device)
+        return self._bufs[key]
+
+    def options(self, width, kernel=capi.KERNEL_AUTO, traversal=capi.TRAVERSAL_AUTO):
+        if self.mode == "tiles" and self.world > 1:
+            return make_options(width, kernel, traversal, self.rank, self.world, self.strip_rows)
+        return make_options(width, kernel, traversal)
+
+    def render_frame(self, camera, level, base_seed, width, height, kernel=capi.KERNEL_AUTO,
+                     traversal=capi.TRAVERSAL_AUTO, d_raster_rgba=0, d_raster_depth=0):
+        """Enqueues one frame on the current stream.  Returns the device tensor that holds the full
+        fp32 RGBA frame on rank 0 (on every rank for "tiles")."""
+        opts = self.options(width, kernel, traversal)
+        win = make_window(self.seed_for_rank(base_seed), height)
+        lv = make_level(level)
+        rows = self.ctx.shard_rows(height, opts)
+        shard = self._buf("shard", (rows, width, 4), torch.float32)
+        self.ctx.render_device(camera, lv, win, opts, d_raster_rgba, d_raster_depth, rgba=shard.data_ptr())
+        if self.world == 1:
+            return shard
+        if self.mode == "samples":
+            dist.reduce(shard, dst=0, op=dist.ReduceOp.SUM)
+            if self.rank == 0:
+                self.ctx.axpby_device(shard.data_ptr(), 1.0 / self.world, shard.data_ptr(), 0.0, shard.numel())
+            return shard
+        gathered = self._buf("gathered", (self.world, rows, width, 4), torch.float32)
+        dist.all_gather_into_tensor(gathered, shard)
+        full = self._buf("full", (height, width, 4), torch.float32)
+        self.ctx.unshard_device(gathered.data_ptr(), rows * width * 4, full.data_ptr(), width, height, 4,
+                                self.world, self.strip_rows)
+        return full
+
+    def close(self):
+        self.ctx.close()

@@ -253,6 +253,10 @@ int bvr_unshard_device(BvrContext* ctx, const void* d_gathered, size_t shard_str
 
 int bvr_get_stats(BvrContext* ctx, BvrStats* out);
 
+/* Measurement helper (not on the render path): FP32 FMA throughput of `device` in TFLOP/s, the
+ * denominator of the FP32 roofline (MEASURED_PEAKS.json has no FP32 figure). */
+int bvr_bench_fp32_peak(int device, float* tflops_out);
+
 #ifdef __cplusplus
 } /* extern "C" */
 
