@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -63,6 +64,11 @@ struct BvrContext {
     bool has_scene = false;
     uint32_t root_ref_host = 0;
     uint32_t tree_depth = 0;
+    uint32_t n_inner = 0;
+    int sm_count = 0;
+    DeviceBuffer pixel_counter;
+    DeviceBuffer wf_state;
+    unsigned int* wf_host_counts = nullptr;   // pinned, 8 words
     PinnedBuffer upload_staging;
     cudaEvent_t upload_done = nullptr;
     bool upload_pending = false;
@@ -103,6 +109,12 @@ bool is_pinned_host(const void* p) {
     return attr.type == cudaMemoryTypeHost;
 }
 
+// tuning knobs for experiments (documented in DESIGN.md); production uses the defaults
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
 uint32_t effective_strip_rows(const BvrRenderOptions* o) { return (o && o->strip_rows) ? o->strip_rows : 8u; }
 
 uint32_t shard_rows_impl(uint32_t height, const BvrRenderOptions* o) {
@@ -118,9 +130,10 @@ uint32_t shard_rows_impl(uint32_t height, const BvrRenderOptions* o) {
 // (raytrace.wgsl:80-87, 313-346): everything reachable from node 0 exactly once, indices in range.
 // Also yields the tree depth (stack bound for the near-first traversal).
 int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, size_t n_materials,
-                   const BvrBvhNode* nodes, size_t n_nodes, uint32_t* depth_out) {
+                   const BvrBvhNode* nodes, size_t n_nodes, uint32_t* depth_out, uint32_t* n_inner_out) {
     (void)models;
     *depth_out = 0;
+    *n_inner_out = 0;
     if (n_models > 0 && n_materials == 0) return fail(ctx, BVR_ERR_BAD_SCENE, "models without materials");
     if (n_models >= (size_t)BVR_LEAF_FIRST_MASK) return fail(ctx, BVR_ERR_BAD_SCENE, "more than 2^24-1 models");
     if (n_nodes == 0) return BVR_OK;
@@ -139,6 +152,7 @@ int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, siz
             if (nd.model_count > BVR_MAX_LEAF_COUNT) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf with more than 128 models");
             if ((size_t)nd.index + nd.model_count > n_models) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf model range out of bounds");
         } else {
+            (*n_inner_out)++;
             if ((size_t)nd.index + 1 >= n_nodes) return fail(ctx, BVR_ERR_BAD_SCENE, "child index out of bounds");
             for (uint32_t c = nd.index; c < nd.index + 2; c++) {
                 if (seen[c]) return fail(ctx, BVR_ERR_BAD_SCENE, "BVH node referenced twice (cycle or DAG)");
@@ -204,7 +218,10 @@ int bvr_create(int device, BvrContext** out_ctx) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->upload_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = ctx->ray_counter.ensure(sizeof(unsigned long long));
     if (e == cudaSuccess) e = ctx->root_ref.ensure(sizeof(uint32_t));
+    if (e == cudaSuccess) e = ctx->pixel_counter.ensure(sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->ray_counter_host, sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->wf_host_counts, 8 * sizeof(unsigned int), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         cudaGetLastError();
         bvr_destroy(ctx);
@@ -223,11 +240,12 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
     if (ctx->ray_counter_host) cudaFreeHost(ctx->ray_counter_host);
+    if (ctx->wf_host_counts) cudaFreeHost(ctx->wf_host_counts);
     cudaEvent_t evs[] = {ctx->ev_render0, ctx->ev_render1, ctx->ev_upload0, ctx->ev_upload1, ctx->upload_done};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -271,8 +289,8 @@ int bvr_upload_scene(BvrContext* ctx,
     if (ranges && !ctx->scene_uploaded)
         return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty ranges given before any full upload");
 
-    uint32_t depth = 0;
-    int st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth);
+    uint32_t depth = 0, n_inner = 0;
+    int st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth, &n_inner);
     if (st != BVR_OK) return st;
 
     // the ranges to copy
@@ -348,6 +366,7 @@ int bvr_upload_scene(BvrContext* ctx,
     ctx->n_materials = n_materials;
     ctx->n_nodes = n_nodes;
     ctx->tree_depth = depth;
+    ctx->n_inner = n_inner;
     ctx->has_scene = n_nodes > 0 && n_models > 0;
     ctx->scene_uploaded = true;
     return BVR_OK;
@@ -441,7 +460,30 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
     if (p.cam.level == 0u) {
         launches += launch_copy_raster(p, ctx->stream);
     } else {
-        launches += launch_megakernel(p, ctx->stream);
+        int n = -1;
+        if (opts->kernel == BVR_KERNEL_WAVEFRONT && !p.reference_order) {
+            const size_t pixels = (size_t)p.cam.width * p.shard.rows;
+            BVR_CK(ctx->wf_state.ensure(wavefront_state_bytes(pixels)));
+            WavefrontParams w;
+            std::memset(&w, 0, sizeof w);
+            w.r = p;
+            wavefront_bind(w, ctx->wf_state.ptr, pixels);
+            w.refill_below = (uint32_t)env_int("BVR_WF_REFILL", 20);
+            n = launch_wavefront(w, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth, ctx->sm_count,
+                                 ctx->wf_host_counts, ctx->stream);
+            if (n < 0) {
+                cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) return fail_cuda(ctx, e, "wavefront pipeline");
+            }
+        }
+        if (n < 0 && !p.reference_order && !env_int("BVR_MK_V1", 0)) {
+            BVR_CK(cudaMemsetAsync(ctx->pixel_counter.ptr, 0, sizeof(unsigned int), ctx->stream));
+            n = launch_megakernel_persistent(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
+                                             ctx->pixel_counter.as<unsigned int>(), env_int("BVR_MK_THREADS", 256),
+                                             (uint32_t)env_int("BVR_MK_WAIT", 8), ctx->sm_count, ctx->stream);
+        }
+        if (n < 0) n = launch_megakernel(p, ctx->stream);   // reference-order traversal, or scene too deep
+        launches += n;
     }
     BVR_CK(cudaGetLastError());
     BVR_CK(cudaEventRecord(ctx->ev_render1, ctx->stream));

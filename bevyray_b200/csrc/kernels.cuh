@@ -30,6 +30,24 @@ struct RenderParams {
     uint32_t reference_order;          // BvrTraversal
 };
 
+// Wavefront path state in HBM (SoA, indexed by shard-local pixel slot) and the work queues.
+struct WavefrontParams {
+    RenderParams r;
+    unsigned int* counters;      // queue sizes + the extend kernel's queue head (wavefront.cu: enum Counter)
+    float4* ray_a;               // (o.x, o.y, o.z, d.x)
+    float4* ray_b;               // (d.y, d.z, hit t, hit model bits)
+    float4* thr_rng;             // (throughput.rgb, rng state bits)
+    float4* accum;               // (sum of gamma-encoded sample colours, sum of first depths)
+    uint4* misc;                 // (sample index, bounce, first_depth bits, -)
+    uint32_t* q_ray[2];          // ping-pong queue of pixel slots with a live ray
+    uint32_t* q_miss;
+    uint32_t* q_metal;
+    uint32_t* q_glass;
+    uint32_t* q_diffuse;
+    uint32_t* q_regen;           // paths that ended: next sample or pixel store
+    uint32_t refill_below;       // extend: refill idle lanes when at most this many lanes are still traversing
+};
+
 // global row of shard-local row `ly`; >= height for padding rows
 __host__ __device__ __forceinline__ uint32_t shard_global_row(const ShardParams& s, uint32_t ly) {
     const uint32_t strip = ly / s.strip_rows;
@@ -52,7 +70,16 @@ int launch_derive_pairs(const RawNode* nodes, uint32_t n_nodes, uint32_t* inner_
                         float4* pairs, uint32_t* root_ref_out, cudaStream_t stream);
 
 // ---- render kernels ----
-int launch_megakernel(const RenderParams& p, cudaStream_t stream);
+int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple one-thread-per-pixel kernel (v1)
+// persistent-lane megakernel; returns -1 when the configuration does not fit (caller falls back to v1)
+int launch_megakernel_persistent(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
+                                 unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, int sm_count,
+                                 cudaStream_t stream);
+size_t wavefront_state_bytes(size_t pixels);
+void wavefront_bind(WavefrontParams& w, void* state, size_t pixels);
+// wavefront pipeline; `host_counts` = 8 pinned words for polling the queue sizes.  -1 = not supported / error
+int launch_wavefront(WavefrontParams w, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth, int sm_count,
+                     volatile unsigned int* host_counts, cudaStream_t stream);
 int launch_copy_raster(const RenderParams& p, cudaStream_t stream);   // level 0: raytrace.wgsl:97-99
 
 // ---- multi-GPU helpers (shard_kernels.cu) ----

@@ -17,6 +17,24 @@ from . import _capi as capi
 from .api import Context, make_level, make_options, make_window
 
 
+def shard_global_rows(height, shard_index, shard_count, strip_rows):
+    """Global row of every shard-local row (>= height for padding rows): the host-side statement of
+    shard_global_row() in csrc/kernels.cuh, used to check / undo the tile sharding."""
+    opts = make_options(1, shard_index=shard_index, shard_count=shard_count, strip_rows=strip_rows)
+    rows = capi.lib.bvr_shard_rows(height, opts)
+    if shard_count <= 1:
+        return np.arange(height)
+    ly = np.arange(rows)
+    return ((ly // strip_rows) * shard_count + shard_index) * strip_rows + (ly % strip_rows)
+
+
+def seed_for_rank(base_seed, rank, world, mode):
+    """Distinct, deterministic random_seed in [0,1) per rank for sample sharding."""
+    if mode != "samples" or world == 1:
+        return float(np.float32(base_seed))
+    return float(np.float32((base_seed + 0.61803398875 * rank) % 1.0))
+
+
 class ShardedRenderer:
     def __init__(self, device, rank=0, world=1, mode="samples", strip_rows=4):
         assert mode in ("tiles", "samples")
@@ -35,10 +53,7 @@ class ShardedRenderer:
         self.ctx.upload_scene(models, materials, nodes, ranges)
 
     def seed_for_rank(self, base_seed):
-        """Distinct, deterministic random_seed in [0,1) per rank for sample sharding."""
-        if self.mode != "samples" or self.world == 1:
-            return float(np.float32(base_seed))
-        return float(np.float32((base_seed + 0.61803398875 * self.rank) % 1.0))
+        return seed_for_rank(base_seed, self.rank, self.world, self.mode)
 
     def _buf(self, name, shape, dtype):
         key = (name, tuple(shape), dtype)

@@ -30,14 +30,15 @@ def assert_planes_equal(got, want, rows=None):
     assert psnr >= PSNR_MIN
 
 
-@pytest.mark.parametrize("traversal", [0, 1])
-def test_c1_default_scene_bit_exact(bvr, oracle, ctx, rtiow, traversal):
+@pytest.mark.parametrize("kernel,traversal", [(1, 0), (1, 1), (2, 0)],
+                         ids=["megakernel-near-first", "megakernel-reference-order", "wavefront"])
+def test_c1_default_scene_bit_exact(bvr, oracle, ctx, rtiow, kernel, traversal):
     """BASELINE.json configs[0]: default scene + camera (src/main.rs:55-70), 1280x720, 1 spp, 4 bounces."""
     W, H = 1280, 720
     cam = bvr.make_camera(sample_count=1, bounces=4, aspect=W / H)
     win = bvr.make_window(0.37, H)
     ctx.upload_scene(rtiow.models, rtiow.materials, rtiow.nodes)
-    got = ctx.render(cam, 3, win, bvr.make_options(W, traversal=traversal))
+    got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=kernel, traversal=traversal))
     want, cnt = oracle.render(rtiow.models, rtiow.materials, rtiow.nodes, cam, bvr.make_level(3), win, W)
     assert_planes_equal(got, want)
     st = ctx.stats()
