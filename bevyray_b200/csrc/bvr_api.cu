@@ -478,9 +478,15 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
         }
         if (n < 0 && !p.reference_order && !env_int("BVR_MK_V1", 0)) {
             BVR_CK(cudaMemsetAsync(ctx->pixel_counter.ptr, 0, sizeof(unsigned int), ctx->stream));
-            n = launch_megakernel_persistent(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
-                                             ctx->pixel_counter.as<unsigned int>(), env_int("BVR_MK_THREADS", 256),
-                                             (uint32_t)env_int("BVR_MK_WAIT", 8), ctx->sm_count, ctx->stream);
+            if (env_int("BVR_MK_VARIANT", 3) == 3)
+                n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
+                                         ctx->pixel_counter.as<unsigned int>(), env_int("BVR_MK_THREADS", 1024),
+                                         (uint32_t)env_int("BVR_MK_WAIT", 26), (uint32_t)env_int("BVR_MK_LEAF", 4),
+                                         ctx->sm_count, ctx->stream);
+            else
+                n = launch_megakernel_persistent(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
+                                                 ctx->pixel_counter.as<unsigned int>(), env_int("BVR_MK_THREADS", 1024),
+                                                 (uint32_t)env_int("BVR_MK_WAIT", 28), ctx->sm_count, ctx->stream);
         }
         if (n < 0) n = launch_megakernel(p, ctx->stream);   // reference-order traversal, or scene too deep
         launches += n;

@@ -75,6 +75,10 @@ int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple o
 int launch_megakernel_persistent(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                                  unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, int sm_count,
                                  cudaStream_t stream);
+// staged-shading persistent megakernel (v3); same contract as launch_megakernel_persistent
+int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
+                         unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
+                         int sm_count, cudaStream_t stream);
 size_t wavefront_state_bytes(size_t pixels);
 void wavefront_bind(WavefrontParams& w, void* state, size_t pixels);
 // wavefront pipeline; `host_counts` = 8 pinned words for polling the queue sizes.  -1 = not supported / error

@@ -1,0 +1,405 @@
+// megakernel_v3.cu — persistent-lane megakernel with STAGED shading and postponed leaf tests.
+//
+// Same lane/pixel ownership, pixel queue and shared-memory staging as megakernel_persistent.cu (v2);
+// what changes is how divergent work is regrouped inside the warp (ncu on v2: 10 of 32 lanes active per
+// instruction, shading and sphere tests running at 4-5 lanes — profiles/r01_v2_*):
+//
+//   * phase A is cut into stages that every waiting lane walks through together, each stage having ONE
+//     code site per expensive operation: classification draws (raytrace.wgsl:234,248) -> one shared
+//     rejection loop for all unit-ball samples (random.wgsl:17-26; diffuse needs two, metal one) -> one
+//     normalize site shared by the miss path (background_gradient) and the hit record -> one normalize
+//     site shared by metal and glass -> per-material direction -> path bookkeeping -> one ray-generation
+//     site -> one ray-setup site;
+//   * phase B postpones sphere tests: a lane that reaches a leaf parks it and keeps walking; parked
+//     leaves are tested together once enough lanes hold one (or a lane cannot continue without it).
+//     Testing a sphere later never changes the closest hit; it only delays culling.
+//
+// Arithmetic of everything that reaches the image is the strict set of trace.cuh (bit-identical to the
+// oracle); box tests use FMA + FMNMX3 (culling only).
+
+#include "kernels.cuh"
+
+namespace bvr {
+
+namespace {
+
+enum LaneState : int { NEED_PIXEL = 0, NEW_PATH = 1, RAY_READY = 2, TRAVERSE = 3, SHADE = 4, DONE = 5 };
+enum Kind : int { K_NONE = 0, K_MISS = 1, K_METAL = 2, K_GLASS = 3, K_DIFFUSE = 4 };
+
+#define V3_NONE 0x7fffffffu
+
+// Explicit 32-bit shared-window addressing: keeps the per-step address math at one IMAD instead of the
+// generic-to-shared conversion the compiler re-derives every time (ncu r01_v3a: 18 instructions per push).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+// Slab test folded for culling: entry = max(lo.x, lo.y, lo.z, 0), exit = min(hi.x, hi.y, hi.z, closest);
+// the box is worth visiting iff entry <= exit.  6 FFMA + 6 FMNMX + 2 FMNMX + 2 FMNMX3 + 1 FSETP.
+__device__ __forceinline__ bool box_cull(V3 inv, V3 noi, float closest_t, float mnx, float mny, float mnz, float mxx,
+                                         float mxy, float mxz, float& entry) {
+    const float t0x = __fmaf_rn(mnx, inv.x, noi.x), t1x = __fmaf_rn(mxx, inv.x, noi.x);
+    const float t0y = __fmaf_rn(mny, inv.y, noi.y), t1y = __fmaf_rn(mxy, inv.y, noi.y);
+    const float t0z = __fmaf_rn(mnz, inv.z, noi.z), t1z = __fmaf_rn(mxz, inv.z, noi.z);
+    entry = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    const float exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), closest_t));
+    return entry <= exit;
+}
+
+struct Tuning {
+    uint32_t shade_wait_lanes;   // leave phase B when this many lanes wait for shading
+    uint32_t leaf_batch_lanes;   // test parked leaves when this many lanes hold one
+};
+
+template <int THREADS, bool SMEM_SCENE>
+__global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, unsigned int* __restrict__ pixel_counter,
+                                                         const uint32_t n_inner, const uint32_t n_models,
+                                                         const Tuning tune) {
+    extern __shared__ float4 smem[];
+    const CameraParams& cam = p.cam;
+    const unsigned full = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+
+    SceneView sv = p.scene;
+    float4* sm_cursor = smem;
+    if (SMEM_SCENE) {
+        float4* sm_pairs = sm_cursor;     sm_cursor += 4u * n_inner;
+        float4* sm_spheres = sm_cursor;   sm_cursor += n_models;
+        float4* sm_materials = sm_cursor; sm_cursor += 2u * sv.n_materials;
+        uint32_t* sm_matid = reinterpret_cast<uint32_t*>(sm_cursor);
+        sm_cursor += (n_models + 3u) / 4u;
+        for (uint32_t i = tid; i < 4u * n_inner; i += THREADS) sm_pairs[i] = p.scene.pairs[i];
+        for (uint32_t i = tid; i < n_models; i += THREADS) sm_spheres[i] = p.scene.spheres[i];
+        for (uint32_t i = tid; i < 2u * sv.n_materials; i += THREADS) sm_materials[i] = p.scene.materials[i];
+        for (uint32_t i = tid; i < n_models; i += THREADS) sm_matid[i] = p.scene.sphere_material[i];
+        sv.pairs = sm_pairs;
+        sv.spheres = sm_spheres;
+        sv.materials = sm_materials;
+        sv.sphere_material = sm_matid;
+        __syncthreads();
+    }
+    // per-lane stack: entry k of lane t at s_stack0 + k * STACK_STRIDE (interleaved: conflict-free)
+    constexpr uint32_t STACK_STRIDE = THREADS * 8u;
+    const uint32_t s_stack0 = smem_addr(sm_cursor) + tid * 8u;
+    const uint32_t s_pairs = SMEM_SCENE ? smem_addr(sv.pairs) : 0u;
+
+    const uint32_t tiles_x = (cam.width + 7u) / 8u, tiles_y = (p.shard.rows + 3u) / 4u;
+    const uint32_t total_slots = tiles_x * tiles_y * 32u;
+
+    int state = NEED_PIXEL;
+    uint32_t px = 0, ly = 0;
+    float u = 0.0f, v = 0.0f;
+    uint32_t rng = 0, sidx = 0, bounce = 0;
+    V3 total = v3(0.0f, 0.0f, 0.0f);
+    float total_depth = 0.0f, first_depth = BVR_INF;
+    uint32_t primary_id = 0xffffffffu;
+    float primary_t = BVR_INF;
+    V3 throughput = v3(1.0f, 1.0f, 1.0f);
+    Ray ray{v3(0, 0, 0), v3(0, 0, 1)};
+    V3 inv = v3(0, 0, 0), noi = v3(0, 0, 0);
+    float a = 1.0f;
+    Hit closest{BVR_INF, 0xffffffffu};
+    uint32_t cur = V3_NONE, pending = V3_NONE;
+    uint32_t sp_addr = s_stack0;   // next free stack slot
+    unsigned long long rays = 0;
+
+    for (;;) {
+        // ======================= phase A: staged shading =======================
+        if (__any_sync(full, state == SHADE)) {
+            // --- A1: classification (raytrace.wgsl:193-201, 232-248) ---
+            int kind = K_NONE;
+            uint32_t mid = 0;
+            if (state == SHADE) {
+                if (bounce == 0u) {
+                    first_depth = closest.t;
+                    if (sidx == 0u) { primary_id = closest.t == BVR_INF ? 0xffffffffu : closest.model; primary_t = closest.t; }
+                }
+                if (closest.t == BVR_INF) {
+                    kind = K_MISS;
+                } else {
+                    mid = sv.sphere_material[closest.model];
+                    if (mid >= sv.n_materials) mid = sv.n_materials - 1u;
+                    const float metallic = sv.materials[2u * mid].w;
+                    const float transmission = sv.materials[2u * mid + 1u].w;
+                    if (rng_next_float(rng) < metallic) kind = K_METAL;
+                    else if (rng_next_float(rng) < transmission) kind = K_GLASS;
+                    else kind = K_DIFFUSE;
+                }
+            }
+            // --- A2: every unit-ball sample of this round in one rejection loop (random.wgsl:17-26) ---
+            int need = kind == K_DIFFUSE ? 2 : (kind == K_METAL ? 1 : 0);
+            V3 b1 = v3(0.0f, 0.0f, 0.0f), b2 = v3(0.0f, 0.0f, 0.0f);
+            while (need > 0) {
+                const float x = rng_next_float(rng);
+                const float y = rng_next_float(rng);
+                const float z = rng_next_float(rng);
+                const V3 c = v3(fsub(fmul(2.0f, x), 1.0f), fsub(fmul(2.0f, y), 1.0f), fsub(fmul(2.0f, z), 1.0f));
+                if (vdot(c, c) <= 1.0f) {
+                    if (need == 2) b1 = c; else b2 = c;   // diffuse: b1 then b2; metal: b2 only
+                    need--;
+                }
+            }
+            // --- A3: hit record / background share one normalize site ---
+            bool path_end = false;
+            V3 sample_color = v3(0.0f, 0.0f, 0.0f);
+            if (state == SHADE) {
+                const float4 sph = kind == K_MISS ? make_float4(0.f, 0.f, 0.f, 0.f) : sv.spheres[closest.model];
+                const V3 position = vadd(ray.o, vscale(closest.t, ray.d));            // ray_at, raytrace.wgsl:130-132
+                const V3 nin = kind == K_MISS ? ray.d : vsub(position, v3(sph.x, sph.y, sph.z));
+                const V3 unit = vnormalize(nin);
+                if (kind == K_MISS) {
+                    // background_gradient, raytrace.wgsl:364-369
+                    const float aa = fmul(0.5f, fadd(unit.y, 1.0f));
+                    const float ia = fsub(1.0f, aa);
+                    const V3 bg = v3(fadd(fmul(ia, 1.0f), fmul(aa, 0.5f)), fadd(fmul(ia, 1.0f), fmul(aa, 0.7f)),
+                                     fadd(fmul(ia, 1.0f), fmul(aa, 1.0f)));
+                    const V3 lin = vmul(throughput, bg);
+                    sample_color = v3(fsqrt(lin.x), fsqrt(lin.y), fsqrt(lin.z));       // raytrace.wgsl:223
+                    path_end = true;
+                } else {
+                    const V3 normal = unit;                                            // raytrace.wgsl:357
+                    const float4 m0 = sv.materials[2u * mid], m1 = sv.materials[2u * mid + 1u];
+                    V3 attenuation = v3(m0.x, m0.y, m0.z);
+                    V3 dir;
+                    bool absorbed;
+                    if (kind == K_DIFFUSE) {                                           // raytrace.wgsl:283-298
+                        dir = vadd(vadd(normal, b1), vscale(m1.x, b2));
+                        if (vec3_near_zero(dir)) dir = normal;
+                        absorbed = vdot(dir, normal) < 0.0f;
+                    } else {
+                        // metal and glass share the second normalize site
+                        const V3 un = vnormalize(kind == K_METAL ? reflect3(ray.d, normal) : ray.d);
+                        if (kind == K_METAL) {                                         // raytrace.wgsl:234-246
+                            dir = vadd(un, vscale(m1.x, b2));
+                            absorbed = vdot(dir, normal) < 0.0f;
+                        } else {                                                       // raytrace.wgsl:248-282
+                            const bool front_face = vdot(ray.d, normal) < 0.0f;
+                            const float ri = front_face ? fdiv(1.0f, m1.z) : m1.z;
+                            const float cos_theta = fminf(vdot(vneg(un), normal), 1.0f);
+                            const float sin_theta = fsqrt(fsub(1.0f, fmul(cos_theta, cos_theta)));
+                            const bool cannot_refract = fmul(ri, sin_theta) > 1.0f;
+                            if (cannot_refract || schlick_reflectance(cos_theta, ri) > rng_next_float(rng)) dir = reflect3(un, normal);
+                            else dir = refract3(un, normal, ri);
+                            attenuation = v3(1.0f, 1.0f, 1.0f);
+                            absorbed = false;
+                        }
+                    }
+                    ray.o = position;
+                    ray.d = dir;
+                    if (absorbed) {
+                        path_end = true;                                               // raytrace.wgsl:207-209
+                    } else {
+                        throughput = vmul(throughput, attenuation);
+                        bounce++;
+                        if (bounce > cam.bounce_count) path_end = true;                // raytrace.wgsl:214-216
+                    }
+                }
+                if (path_end) {
+                    if (first_depth == BVR_INF) first_depth = cam.fallback_far;
+                    total = vadd(total, sample_color);
+                    total_depth = fadd(total_depth, first_depth);
+                    sidx++;
+                    state = NEW_PATH;
+                } else {
+                    state = RAY_READY;
+                }
+            }
+        }
+        // --- A4: pixel store (average, fused composite raytrace.wgsl:104-120) ---
+        if (state == NEW_PATH && sidx >= cam.sample_count) {
+            const uint32_t gy = shard_global_row(p.shard, ly);
+            const float n = (float)cam.sample_count;
+            float4 out = make_float4(fdiv(total.x, n), fdiv(total.y, n), fdiv(total.z, n), 1.0f);
+            const float depth_avg = fdiv(total_depth, n);
+            if (cam.level == 1u || cam.level == 2u) {
+                const size_t gpix = (size_t)gy * cam.width + px;
+                if (raster_wins(cam, p.raster_depth[gpix], depth_avg)) out = p.raster_rgba[gpix];
+            }
+            const size_t lpix = (size_t)ly * cam.width + px;
+            if (p.out_rgba) p.out_rgba[lpix] = out;
+            if (p.out_rt_depth) p.out_rt_depth[lpix] = depth_avg;
+            if (p.out_primary_id) p.out_primary_id[lpix] = primary_id;
+            if (p.out_primary_depth) p.out_primary_depth[lpix] = primary_t;
+            if (p.out_srgb8) p.out_srgb8[lpix] = store_srgb8(out);
+            state = NEED_PIXEL;
+        }
+        // --- A5: pull new pixels from the tile-ordered queue (warp-convergent) ---
+        for (;;) {
+            const unsigned need_px = __ballot_sync(full, state == NEED_PIXEL);
+            if (need_px == 0u) break;
+            const int leader = __ffs(need_px) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(pixel_counter, (unsigned)__popc(need_px));
+            base = __shfl_sync(full, base, leader);
+            if (state == NEED_PIXEL) {
+                const uint32_t slot = base + (uint32_t)__popc(need_px & ((1u << lane) - 1u));
+                if (slot >= total_slots) {
+                    state = DONE;
+                } else {
+                    const uint32_t tile = slot >> 5, within = slot & 31u;
+                    px = (tile % tiles_x) * 8u + (within & 7u);
+                    ly = (tile / tiles_x) * 4u + (within >> 3);
+                    const uint32_t gy = shard_global_row(p.shard, ly);
+                    if (px < cam.width && ly < p.shard.rows && gy < cam.height) {
+                        u = pixel_u(cam, px);
+                        v = pixel_v(cam, gy);
+                        rng = pixel_seed(cam, u, v);
+                        sidx = 0u;
+                        total = v3(0.0f, 0.0f, 0.0f);
+                        total_depth = 0.0f;
+                        primary_id = 0xffffffffu;
+                        primary_t = BVR_INF;
+                        state = NEW_PATH;
+                    }
+                }
+            }
+        }
+        if (__all_sync(full, state == DONE)) break;
+        // --- A6: camera rays (raytrace.wgsl:139-156), one site ---
+        if (state == NEW_PATH && sidx < cam.sample_count) {
+            ray = random_ray_from_uv(cam, u, v, rng);
+            throughput = v3(1.0f, 1.0f, 1.0f);
+            bounce = 0u;
+            first_depth = BVR_INF;
+            state = RAY_READY;
+        }
+        // --- A7: ray setup, one site for camera rays and scattered rays ---
+        if (state == RAY_READY) {
+            inv = v3(fdiv(1.0f, ray.d.x), fdiv(1.0f, ray.d.y), fdiv(1.0f, ray.d.z));
+            noi = v3(-fmul(ray.o.x, inv.x), -fmul(ray.o.y, inv.y), -fmul(ray.o.z, inv.z));
+            a = vdot(ray.d, ray.d);
+            closest.t = BVR_INF;
+            closest.model = 0xffffffffu;
+            sp_addr = s_stack0;
+            pending = V3_NONE;
+            cur = sv.has_scene ? sv.root_ref : V3_NONE;
+            rays++;
+            state = TRAVERSE;
+        }
+
+        // ======================= phase B: traversal =======================
+        for (;;) {
+            bool blocked = false;
+#pragma unroll
+            for (int rep = 0; rep < 2; rep++) {
+                if (state == TRAVERSE) {
+                    uint32_t c = cur;
+                    if (c < V3_NONE) {                       // inner node: test both children
+                        float4 q0, q1, q2;
+                        uint32_t r0, r1;
+                        if (SMEM_SCENE) {
+                            const uint32_t na = s_pairs + c * 64u;
+                            q0 = lds128(na); q1 = lds128(na + 16u); q2 = lds128(na + 32u);
+                            const uint2 rr = lds64(na + 48u);
+                            r0 = rr.x; r1 = rr.y;
+                        } else {
+                            const float4* nd = sv.pairs + 4u * c;
+                            q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2);
+                            const float4 q3 = __ldg(nd + 3);
+                            r0 = __float_as_uint(q3.x); r1 = __float_as_uint(q3.y);
+                        }
+                        float d0, d1;
+                        const bool h0 = box_cull(inv, noi, closest.t, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, d0);
+                        const bool h1 = box_cull(inv, noi, closest.t, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, d1);
+                        const bool first0 = d0 < d1;         // ties go to the second child (reference LIFO order)
+                        if (h0 && h1) {
+                            sts64(sp_addr, first0 ? r1 : r0, __float_as_uint(first0 ? d1 : d0));
+                            sp_addr += STACK_STRIDE;
+                            c = first0 ? r0 : r1;
+                        } else {
+                            c = h0 ? r0 : (h1 ? r1 : V3_NONE);
+                        }
+                    }
+                    if ((int)c < 0) {                        // leaf: park it, or wait for the batch test
+                        if (pending == V3_NONE) { pending = c; c = V3_NONE; }
+                        else blocked = true;
+                    }
+                    if (c == V3_NONE) {
+                        if (sp_addr != s_stack0) {
+                            sp_addr -= STACK_STRIDE;
+                            const uint2 e = lds64(sp_addr);
+                            if (__uint_as_float(e.y) < closest.t) c = e.x;
+                        } else if (pending == V3_NONE) {
+                            state = SHADE;                   // traversal finished
+                        } else {
+                            blocked = true;                  // only the parked leaf is left
+                        }
+                    }
+                    cur = c;
+                }
+            }
+            // batched sphere tests: once enough lanes cannot continue without theirs (or none can continue)
+            const unsigned blk = __ballot_sync(full, blocked);
+            const unsigned trav = __ballot_sync(full, state == TRAVERSE);
+            if (trav == 0u) break;
+            const uint32_t nblk = (uint32_t)__popc(blk), ntrav = (uint32_t)__popc(trav);
+            if (nblk >= tune.leaf_batch_lanes || nblk == ntrav) {
+                if (state == TRAVERSE && pending != V3_NONE) {
+                    test_leaf(sv, ray, a, pending, closest);
+                    pending = V3_NONE;
+                }
+            }
+            if (32u - ntrav >= tune.shade_wait_lanes) {
+                // lanes outside TRAVERSE are waiting to shade or out of pixels; only the former justify phase A
+                const unsigned waiting = __ballot_sync(full, state == SHADE);
+                if ((uint32_t)__popc(waiting) >= tune.shade_wait_lanes) break;
+            }
+        }
+    }
+
+    unsigned long long sum = rays;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
+    if (lane == 0u && p.ray_counter && sum) atomicAdd(p.ray_counter, sum);
+}
+
+template <int THREADS>
+int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
+              unsigned int* pixel_counter, Tuning tune, int sm_count, cudaStream_t stream) {
+    const uint32_t stack_cap = tree_depth + 1u;
+    const size_t scene_bytes = (size_t)(4u * n_inner + n_models + 2u * p.scene.n_materials + (n_models + 3u) / 4u) * 16u;
+    const size_t stack_bytes = (size_t)THREADS * stack_cap * sizeof(uint2);
+    const size_t max_smem = 227u * 1024u;
+    const bool smem_scene = scene_bytes + stack_bytes <= max_smem;
+    const size_t smem = (smem_scene ? scene_bytes : 0) + stack_bytes;
+    if (smem > max_smem) return -1;
+    auto kern = smem_scene ? megakernel_v3<THREADS, true> : megakernel_v3<THREADS, false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int blocks_per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
+        return -1;
+    const uint32_t tiles = ((p.cam.width + 7u) / 8u) * ((p.shard.rows + 3u) / 4u);
+    uint32_t grid = (uint32_t)(sm_count * blocks_per_sm);
+    const uint32_t max_useful = (tiles * 32u + THREADS - 1u) / THREADS;
+    if (grid > max_useful) grid = max_useful;
+    if (grid == 0) return 0;
+    kern<<<grid, THREADS, smem, stream>>>(p, pixel_counter, n_inner, n_models, tune);
+    return 1;
+}
+
+}  // namespace
+
+int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
+                         unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
+                         int sm_count, cudaStream_t stream) {
+    Tuning t{shade_wait_lanes, leaf_batch_lanes};
+    switch (threads) {
+        case 256: return launch_v3<256>(p, n_inner, n_models, tree_depth, pixel_counter, t, sm_count, stream);
+        case 512: return launch_v3<512>(p, n_inner, n_models, tree_depth, pixel_counter, t, sm_count, stream);
+        case 1024: return launch_v3<1024>(p, n_inner, n_models, tree_depth, pixel_counter, t, sm_count, stream);
+        default: return -1;
+    }
+}
+
+}  // namespace bvr
