@@ -20,6 +20,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/s, RTIOW final scene 1920x1080 100 spp 10 bounces (ray = one raycast() call, raytrace.wgsl:190)"
+METRIC_C4 = "Mrays/s, synthetic 2^20 random spheres 1920x1080 64 spp 10 bounces (ray = one raycast() call)"
 UNIT = "Mrays/s"
 SCENE_SEED = 1
 BASE_SEED = 0.37
@@ -28,6 +29,10 @@ WORKLOADS = {
     # BASELINE.json configs[1]: RTIOW book-1 final scene, 1920x1080, 100 spp, 10 bounces, level Pure
     "c2": dict(name="C2 rtiow-final 1920x1080 100spp 10 bounces, book camera (13,2,3)->(0,0,0) vfov 20deg",
                width=1920, height=1080, spp=100, bounces=10, camera="book"),
+    # BASELINE.json configs[3]: traversal / memory-bound stress, scene does not fit in shared memory
+    "c4": dict(name="C4 synthetic 2^20 random spheres (cube side 200, r in [0.05,0.25], 80/15/5 % materials), "
+                    "1920x1080 64spp 10 bounces, camera (0,0,130)->(0,0,0) fov pi/4",
+               width=1920, height=1080, spp=64, bounces=10, camera="c4", scene=("random", 7, 1 << 20, 200.0, 0.05, 0.25)),
     # BASELINE.json configs[0] (plumbing / parity case)
     "c1": dict(name="C1 default scene 1280x720 1spp 4 bounces, repo camera (0,0,5)->(0,0,0) fov pi/4",
                width=1280, height=720, spp=1, bounces=4, camera="repo"),
@@ -37,10 +42,20 @@ WORKLOADS = {
 def make_cam(bvr, wl, spp=None):
     aspect = wl["width"] / wl["height"]
     spp = wl["spp"] if spp is None else spp
+    if wl["camera"] == "c4":
+        return bvr.make_camera(position=(0.0, 0.0, 130.0), target=(0.0, 0.0, 0.0), aspect=aspect, sample_count=spp,
+                               bounces=wl["bounces"])
     if wl["camera"] == "book":
         return bvr.make_camera(position=(13.0, 2.0, 3.0), target=(0.0, 0.0, 0.0), fov=float(np.deg2rad(20.0)),
                                aspect=aspect, sample_count=spp, bounces=wl["bounces"])
     return bvr.make_camera(aspect=aspect, sample_count=spp, bounces=wl["bounces"])
+
+
+def make_scene(bvr, wl):
+    sc = wl.get("scene")
+    if sc and sc[0] == "random":
+        return bvr.Scene.random(*sc[1:])
+    return bvr.Scene.rtiow(SCENE_SEED)
 
 
 def flops_per_ray(cnt):
@@ -118,7 +133,7 @@ def run_reference(args):
     import bevyray_b200 as bvr
     from oracle import oracle
     wl = WORKLOADS[args.workload]
-    scene = bvr.Scene.rtiow(SCENE_SEED)
+    scene = make_scene(bvr, wl)
     sample_spp = max(1, min(wl["spp"], args.cpu_spp))
     cores = oracle.max_threads()
     for _ in range(args.warmup):
@@ -130,7 +145,7 @@ def run_reference(args):
         total += dt
     value = rays / total / 1e6
     sample = f"{wl['width']}x{wl['height']} x {sample_spp} spp of {wl['spp']} per step (same scene, camera, seed, bounces)"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC_C4 if args.workload == "c4" else METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3 * (wl["spp"] / sample_spp),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "l2": "not applicable (CPU)",
@@ -160,9 +175,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = WORKLOADS[args.workload]
     W, H = wl["width"], wl["height"]
-    scene = bvr.Scene.rtiow(SCENE_SEED)
+    scene = make_scene(bvr, wl)
     cam = make_cam(bvr, wl)
-    kernel = {"auto": capi.KERNEL_AUTO, "megakernel": capi.KERNEL_MEGAKERNEL, "wavefront": capi.KERNEL_WAVEFRONT}[args.kernel]
+    kernel = {"auto": capi.KERNEL_AUTO, "megakernel": capi.KERNEL_MEGAKERNEL, "wavefront": capi.KERNEL_WAVEFRONT,
+              "cta-wavefront": capi.KERNEL_CTA_WAVEFRONT}[args.kernel]
     traversal = capi.TRAVERSAL_REFERENCE_ORDER if args.reference_order else capi.TRAVERSAL_AUTO
 
     r = ShardedRenderer(local_rank, rank, world, mode=args.shard, strip_rows=args.strip_rows)
@@ -256,7 +272,7 @@ def run_ours(args):
     e2e_value = e2e_rays / e2e_s / 1e6
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC_C4 if args.workload == "c4" else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak" if args.shard == "samples" else "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -294,7 +310,7 @@ def run_ours(args):
                     traffic = json.load(open(tpath)).get(args.workload)
                 except Exception:
                     traffic = None
-            line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+            fp32_roof = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                                 "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
                                 "peak_source": "measured live: bvr_bench_fp32_peak FFMA probe (MEASURED_PEAKS.json has no FP32 figure)",
                                 "flops_per_ray": fpr, "kernel_ms": avg_kernel_s * 1e3,
@@ -309,14 +325,92 @@ def run_ours(args):
             hbm_peak_src = "measured (MEASURED_PEAKS.json)" if hbm_peak else "fallback (B200_PROFILING.md)"
             hbm_peak = hbm_peak or 6650.0
             hbm_achieved = bpr * rays_per_launch / avg_kernel_s / 1e9
-            line["roofline_hbm"] = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+            hbm_roof = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": hbm_achieved / hbm_peak, "traffic": traffic, "bytes_per_ray": bpr,
                                     "peak_source": hbm_peak_src,
-                                    "note": "scene is smem/L1/L2 resident on this workload; HBM is not the bound"}
+                                    "note": "reference-layout bytes each fetched once; on C2 they are served from shared memory "
+                                            "(HBM is not the bound), on C4 from L2/HBM"}
+            # the scene of C4 (160 MB in reference layout) exceeds shared memory and L2: node fetches bound it
+            if args.workload == "c4":
+                line["roofline"], line["roofline_fp32"] = hbm_roof, fp32_roof
+            else:
+                line["roofline"], line["roofline_hbm"] = fp32_roof, hbm_roof
         print(json.dumps(line), flush=True)
     r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_c5(args):
+    """BASELINE.json configs[4]: animated 10k-sphere scene, per-frame BVH rebuild (host PLOC), dirty-range upload,
+    render at the demo defaults (4 spp, 4 bounces, level FallbackRaytraced) with the fused depth composite
+    against a synthetic raster colour/depth.  Reports the per-frame split."""
+    import torch
+
+    import bevyray_b200 as bvr
+    from bevyray_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — bevyray_b200 has no CPU fallback")
+    W, H, frames = 1280, 720, args.frames
+    scene = bvr.Scene.random(11, 10000, 43.0, 0.05, 0.25)
+    cam = bvr.make_camera(position=(0.0, 0.0, 40.0), target=(0.0, 0.0, 0.0), aspect=W / H, sample_count=4, bounces=4)
+    ctx = bvr.Context(0)
+    rs = np.random.RandomState(0)
+    raster = torch.from_numpy(rs.rand(H, W, 4).astype(np.float32)).pin_memory().numpy()
+    depth = torch.from_numpy((rs.rand(H, W) * 0.004).astype(np.float32)).pin_memory().numpy()
+    out = {"rgba": torch.empty((H, W, 4), dtype=torch.float32).pin_memory().numpy()}
+    opts = bvr.make_options(W)
+    ctx.upload_scene(scene.models, scene.materials, scene.nodes)
+    prev_models, prev_nodes = scene.models.copy(), scene.nodes.copy()
+    t_build = t_upload = t_render = 0.0
+    rays = h2d = 0
+    t_all0 = time.perf_counter()
+    for f in range(frames):
+        t0 = time.perf_counter()
+        scene.animate(f + 1)                                  # closed-form motion + PLOC rebuild (host)
+        t1 = time.perf_counter()
+        m, n = scene.models, scene.nodes
+        # dirty ranges: changed models, and the span of changed BVH nodes
+        dm = np.nonzero((m.view(np.uint8).reshape(-1, 32) != prev_models.view(np.uint8).reshape(-1, 32)).any(axis=1))[0]
+        dn = np.nonzero((n.view(np.uint8).reshape(-1, 48) != prev_nodes.view(np.uint8).reshape(-1, 48)).any(axis=1))[0]
+        ranges = []
+        if len(dm):
+            # runs of consecutive dirty models, bridged over gaps < 16
+            start = prev = int(dm[0])
+            for i in dm[1:]:
+                i = int(i)
+                if i - prev > 16:
+                    ranges.append((capi.ARRAY_MODELS, start, prev - start + 1))
+                    start = i
+                prev = i
+            ranges.append((capi.ARRAY_MODELS, start, prev - start + 1))
+        if len(dn):
+            ranges.append((capi.ARRAY_BVH_NODES, int(dn.min()), int(dn.max() - dn.min() + 1)))
+        st0 = ctx.stats()["h2d_bytes"]
+        ctx.upload_scene(m, scene.materials, n, ranges)
+        h2d += ctx.stats()["h2d_bytes"] - st0
+        prev_models, prev_nodes = m.copy(), n.copy()
+        t2 = time.perf_counter()
+        ctx.render(cam, 2, bvr.make_window((0.37 + 0.013 * f) % 1.0, H), opts, raster, depth, want=("rgba",), out=out)
+        t3 = time.perf_counter()
+        st = ctx.stats()
+        rays += st["rays"]
+        t_build += t1 - t0
+        t_upload += t2 - t1
+        t_render += t3 - t2
+    total = time.perf_counter() - t_all0
+    line = {"metric": "frame ms, animated 10k spheres 1280x720 4spp 4 bounces level 2 (BVH rebuild + dirty upload + render + composite)",
+            "value": total / frames * 1e3, "unit": "ms/frame", "n_gpus": 1, "steps": frames, "warmup": 0,
+            "ms_per_step": total / frames * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5 animated 10k random spheres, 300 frames, per-frame host PLOC rebuild, dirty-range upload, "
+                                   "fused depth composite vs synthetic raster"},
+            "split_ms": {"host_bvh_build": t_build / frames * 1e3, "dirty_detect_and_upload": t_upload / frames * 1e3,
+                         "render_with_host_io": t_render / frames * 1e3},
+            "mrays_per_s": rays / total / 1e6, "scene_h2d_bytes_per_frame": h2d / frames,
+            "full_scene_bytes": int(scene.models.nbytes + scene.materials.nbytes + scene.nodes.nbytes)}
+    print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 def main():
@@ -325,8 +419,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "megakernel", "wavefront"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--frames", type=int, default=300, help="frames of the animated workload (c5)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "megakernel", "wavefront", "cta-wavefront"])
     ap.add_argument("--reference-order", action="store_true", help="reference traversal order (raytrace.wgsl:313-346)")
     ap.add_argument("--shard", default="samples", choices=["samples", "tiles"])
     ap.add_argument("--strip-rows", type=int, default=4)
@@ -344,6 +439,10 @@ def main():
     if world != args.gpus and args.impl == "ours":
         if world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if args.workload == "c5":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_c5(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

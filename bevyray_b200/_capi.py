@@ -30,7 +30,7 @@ BVR_ERR_NO_DEVICE = 7
 # BvrRaytracing (src/raytracing/mod.rs:94-101)
 RAYTRACING_SKIP, RAYTRACING_FALLBACK_RASTER, RAYTRACING_FALLBACK_RAYTRACED, RAYTRACING_PURE = 0, 1, 2, 3
 # BvrKernel / BvrTraversal
-KERNEL_AUTO, KERNEL_MEGAKERNEL, KERNEL_WAVEFRONT = 0, 1, 2
+KERNEL_AUTO, KERNEL_MEGAKERNEL, KERNEL_WAVEFRONT, KERNEL_CTA_WAVEFRONT = 0, 1, 2, 3
 TRAVERSAL_AUTO, TRAVERSAL_REFERENCE_ORDER = 0, 1
 ARRAY_MODELS, ARRAY_MATERIALS, ARRAY_BVH_NODES = 0, 1, 2
 

@@ -383,7 +383,7 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     if (level->level > 3u) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "raytrace level > 3");
     if (opts->shard_count > 1 && opts->shard_index >= opts->shard_count)
         return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "shard_index >= shard_count");
-    if (opts->kernel > BVR_KERNEL_WAVEFRONT || opts->traversal > BVR_TRAVERSAL_REFERENCE_ORDER)
+    if (opts->kernel > BVR_KERNEL_CTA_WAVEFRONT || opts->traversal > BVR_TRAVERSAL_REFERENCE_ORDER)
         return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "unknown kernel / traversal");
 
     RenderParams p;
@@ -461,16 +461,23 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
         launches += launch_copy_raster(p, ctx->stream);
     } else {
         int n = -1;
-        if (opts->kernel == BVR_KERNEL_WAVEFRONT && !p.reference_order) {
-            const size_t pixels = (size_t)p.cam.width * p.shard.rows;
-            BVR_CK(ctx->wf_state.ensure(wavefront_state_bytes(pixels)));
+        if ((opts->kernel == BVR_KERNEL_WAVEFRONT || opts->kernel == BVR_KERNEL_CTA_WAVEFRONT) && !p.reference_order) {
+            const bool cta = opts->kernel == BVR_KERNEL_CTA_WAVEFRONT;
+            const size_t slots = cta ? cta_wavefront_slots(ctx->sm_count) : (size_t)p.cam.width * p.shard.rows;
+            BVR_CK(ctx->wf_state.ensure(wavefront_state_bytes(slots)));
             WavefrontParams w;
             std::memset(&w, 0, sizeof w);
             w.r = p;
-            wavefront_bind(w, ctx->wf_state.ptr, pixels);
-            w.refill_below = (uint32_t)env_int("BVR_WF_REFILL", 20);
-            n = launch_wavefront(w, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth, ctx->sm_count,
-                                 ctx->wf_host_counts, ctx->stream);
+            wavefront_bind(w, ctx->wf_state.ptr, slots);
+            w.refill_below = (uint32_t)env_int("BVR_WF_REFILL", 8);
+            if (cta) {
+                BVR_CK(cudaMemsetAsync(ctx->pixel_counter.ptr, 0, sizeof(unsigned int), ctx->stream));
+                n = launch_cta_wavefront(w, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth, ctx->sm_count,
+                                         ctx->pixel_counter.as<unsigned int>(), ctx->stream);
+            } else {
+                n = launch_wavefront(w, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth, ctx->sm_count,
+                                     ctx->wf_host_counts, ctx->stream);
+            }
             if (n < 0) {
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return fail_cuda(ctx, e, "wavefront pipeline");
@@ -478,15 +485,23 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
         }
         if (n < 0 && !p.reference_order && !env_int("BVR_MK_V1", 0)) {
             BVR_CK(cudaMemsetAsync(ctx->pixel_counter.ptr, 0, sizeof(unsigned int), ctx->stream));
-            if (env_int("BVR_MK_VARIANT", 3) == 3)
-                n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
-                                         ctx->pixel_counter.as<unsigned int>(), env_int("BVR_MK_THREADS", 1024),
-                                         (uint32_t)env_int("BVR_MK_WAIT", 26), (uint32_t)env_int("BVR_MK_LEAF", 4),
-                                         ctx->sm_count, ctx->stream);
-            else
-                n = launch_megakernel_persistent(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
-                                                 ctx->pixel_counter.as<unsigned int>(), env_int("BVR_MK_THREADS", 1024),
-                                                 (uint32_t)env_int("BVR_MK_WAIT", 28), ctx->sm_count, ctx->stream);
+            // largest CTA whose stacks (and, when it fits, the scene) fit in shared memory
+            const int forced = env_int("BVR_MK_THREADS", 0);
+            const int candidates[4] = {1024, 768, 512, 256};
+            for (int ci = 0; ci < 4 && n < 0; ci++) {
+                const int threads = forced ? forced : candidates[ci];
+                if (env_int("BVR_MK_VARIANT", 3) == 3)
+                    n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
+                                             ctx->pixel_counter.as<unsigned int>(), threads,
+                                             (uint32_t)env_int("BVR_MK_WAIT", 26), (uint32_t)env_int("BVR_MK_LEAF", 4),
+                                             ctx->sm_count, ctx->stream);
+                else
+                    n = launch_megakernel_persistent(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
+                                                     ctx->pixel_counter.as<unsigned int>(), threads,
+                                                     (uint32_t)env_int("BVR_MK_WAIT", 28), ctx->sm_count, ctx->stream);
+                if (forced) break;
+            }
+            if (n < 0) cudaGetLastError();
         }
         if (n < 0) n = launch_megakernel(p, ctx->stream);   // reference-order traversal, or scene too deep
         launches += n;

@@ -158,17 +158,33 @@ std::vector<BvrBvhNode> build_ploc(const std::vector<BvrModel>& models, uint32_t
     std::vector<uint32_t> nn(n);
     std::vector<Cluster> next(n);
     size_t m = n;
-    const int64_t r = (int64_t)search_distance;
+    const size_t r = (size_t)search_distance;
+    // dist[i*r + (k-1)] = merged half-area of clusters i and i+k: every pair is evaluated once and read
+    // from both sides (the backward neighbours of i are the forward entries of i-k)
+    std::vector<float> dist(n * r);
     while (m > 1) {
-#pragma omp parallel for schedule(static) if (m > 4096)
-        for (int64_t i = 0; i < (int64_t)m; i++) {
+        const int64_t mm = (int64_t)m;
+#pragma omp parallel for schedule(static) if (m > 2048)
+        for (int64_t i = 0; i < mm; i++) {
+            float* di = &dist[(size_t)i * r];
+            const Box& bi = cur[(size_t)i].box;
+            const size_t kmax = std::min(r, (size_t)(mm - 1 - i));
+            for (size_t k = 1; k <= kmax; k++) di[k - 1] = half_area(box_union(bi, cur[(size_t)i + k].box));
+        }
+#pragma omp parallel for schedule(static) if (m > 2048)
+        for (int64_t i = 0; i < mm; i++) {
             float best = std::numeric_limits<float>::infinity();
             uint32_t best_j = 0xffffffffu;
-            const int64_t lo = std::max<int64_t>(0, i - r), hi = std::min<int64_t>((int64_t)m - 1, i + r);
-            for (int64_t j = lo; j <= hi; j++) {
-                if (j == i) continue;
-                float a = half_area(box_union(cur[(size_t)i].box, cur[(size_t)j].box));
-                if (a < best) { best = a; best_j = (uint32_t)j; }
+            // backward neighbours first (lower index wins ties), then forward
+            const size_t kback = std::min(r, (size_t)i);
+            for (size_t k = kback; k >= 1; k--) {
+                const float a = dist[((size_t)i - k) * r + (k - 1)];
+                if (a < best) { best = a; best_j = (uint32_t)((size_t)i - k); }
+            }
+            const size_t kmax = std::min(r, (size_t)(mm - 1 - i));
+            for (size_t k = 1; k <= kmax; k++) {
+                const float a = dist[(size_t)i * r + (k - 1)];
+                if (a < best) { best = a; best_j = (uint32_t)((size_t)i + k); }
             }
             nn[(size_t)i] = best_j;
         }

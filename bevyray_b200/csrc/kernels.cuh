@@ -39,6 +39,7 @@ struct WavefrontParams {
     float4* thr_rng;             // (throughput.rgb, rng state bits)
     float4* accum;               // (sum of gamma-encoded sample colours, sum of first depths)
     uint4* misc;                 // (sample index, bounce, first_depth bits, -)
+    uint32_t* slot_pixel;        // shard-local pixel index rendered in this slot (0xffffffff = empty)
     uint32_t* q_ray[2];          // ping-pong queue of pixel slots with a live ray
     uint32_t* q_miss;
     uint32_t* q_metal;
@@ -79,8 +80,12 @@ int launch_megakernel_persistent(const RenderParams& p, uint32_t n_inner, uint32
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
                          int sm_count, cudaStream_t stream);
-size_t wavefront_state_bytes(size_t pixels);
-void wavefront_bind(WavefrontParams& w, void* state, size_t pixels);
+size_t wavefront_state_bytes(size_t slots);
+void wavefront_bind(WavefrontParams& w, void* state, size_t slots);
+// persistent per-CTA wavefront (cta_wavefront.cu): number of path slots it needs, and the launch
+size_t cta_wavefront_slots(int sm_count);
+int launch_cta_wavefront(WavefrontParams w, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth, int sm_count,
+                         unsigned int* pixel_counter, cudaStream_t stream);
 // wavefront pipeline; `host_counts` = 8 pinned words for polling the queue sizes.  -1 = not supported / error
 int launch_wavefront(WavefrontParams w, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth, int sm_count,
                      volatile unsigned int* host_counts, cudaStream_t stream);

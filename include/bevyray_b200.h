@@ -143,7 +143,8 @@ typedef struct BvrDirtyRange {
 typedef enum BvrKernel {
     BVR_KERNEL_AUTO = 0,        /* library picks (megakernel) */
     BVR_KERNEL_MEGAKERNEL = 1,  /* persistent-thread megakernel */
-    BVR_KERNEL_WAVEFRONT = 2    /* raygen / extend / shade / compact pipeline */
+    BVR_KERNEL_WAVEFRONT = 2,   /* raygen / extend / shade / compact pipeline, one launch per stage */
+    BVR_KERNEL_CTA_WAVEFRONT = 3 /* the same stages inside one persistent kernel, one pool of paths per CTA */
 } BvrKernel;
 
 typedef enum BvrTraversal {

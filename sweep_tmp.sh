@@ -1,4 +1,3 @@
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 2>&1 | tail -2
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 3 --shard tiles 2>&1 | tail -2
-timeout 300 python bench.py --steps 3 --warmup 3 2>&1 | tail -1
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 600 python bench.py --workload c4 --steps 2 --warmup 3 --cpu-spp 1 2>&1 | tail -1
+timeout 600 python bench.py --workload c5 --frames 100 2>&1 | tail -1

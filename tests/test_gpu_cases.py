@@ -9,8 +9,8 @@ from golden_util import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [(1, 0), (1, 1), (2, 0)]
-KERNEL_IDS = ["megakernel-near-first", "megakernel-reference-order", "wavefront"]
+KERNELS = [(1, 0), (1, 1), (2, 0), (3, 0)]
+KERNEL_IDS = ["megakernel-near-first", "megakernel-reference-order", "wavefront", "cta-wavefront"]
 
 
 def bits(a):
@@ -125,6 +125,22 @@ def test_composite_levels(bvr, oracle, ctx, rtiow, level, kernel, traversal):
         assert (got["rgba"] == raster).all(axis=-1).any() and (got["rgba"] != raster).any(axis=-1).any()
 
 
+@pytest.mark.parametrize("kernel,traversal", KERNELS, ids=KERNEL_IDS)
+def test_large_random_scene_global_memory_path(bvr, oracle, ctx, kernel, traversal):
+    """C4-style scene (BASELINE configs[3]) at reduced size: 20k spheres do not fit in shared memory, so the
+    kernels walk the child-pair records in HBM/L2.  Same density as the 2^20-sphere benchmark scene."""
+    scene = bvr.Scene.random(7, 20000, 54.0, 0.05, 0.25)
+    assert bvr.validate_bvh(scene.nodes, scene.models) is None
+    W, H = 192, 108
+    cam = bvr.make_camera(position=(0, 0, 36), target=(0, 0, 0), aspect=W / H, sample_count=2, bounces=6)
+    win = bvr.make_window(0.42, H)
+    ctx.upload_scene(scene.models, scene.materials, scene.nodes)
+    got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=kernel, traversal=traversal))
+    want, cnt = oracle.render(scene.models, scene.materials, scene.nodes, cam, bvr.make_level(3), win, W)
+    check(got, want)
+    assert ctx.stats()["rays"] == cnt["rays"] and cnt["stack_truncations"] == 0
+
+
 def test_srgb8_store(bvr, oracle, ctx, rtiow):
     """Rgba8UnormSrgb store conversion of the colour target (pipeline.rs:311-315), +-1 LSB (powf on device)."""
     W, H = 128, 72
@@ -136,7 +152,7 @@ def test_srgb8_store(bvr, oracle, ctx, rtiow):
     assert (got["srgb8"] == want).mean() > 0.99
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["megakernel", "wavefront"])
+@pytest.mark.parametrize("kernel", [1, 2, 3], ids=["megakernel", "wavefront", "cta-wavefront"])
 @pytest.mark.parametrize("world,strip", [(2, 4), (3, 8), (8, 1)])
 def test_tile_shards_reassemble_bit_exact(bvr, oracle, ctx, rtiow, world, strip, kernel):
     """Tile sharding: the union of all shards equals the unsharded image bit for bit."""

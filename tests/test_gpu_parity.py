@@ -30,8 +30,8 @@ def assert_planes_equal(got, want, rows=None):
     assert psnr >= PSNR_MIN
 
 
-@pytest.mark.parametrize("kernel,traversal", [(1, 0), (1, 1), (2, 0)],
-                         ids=["megakernel-near-first", "megakernel-reference-order", "wavefront"])
+@pytest.mark.parametrize("kernel,traversal", [(1, 0), (1, 1), (2, 0), (3, 0)],
+                         ids=["megakernel-near-first", "megakernel-reference-order", "wavefront", "cta-wavefront"])
 def test_c1_default_scene_bit_exact(bvr, oracle, ctx, rtiow, kernel, traversal):
     """BASELINE.json configs[0]: default scene + camera (src/main.rs:55-70), 1280x720, 1 spp, 4 bounces."""
     W, H = 1280, 720
