@@ -182,7 +182,10 @@ def run_ours(args):
     traversal = capi.TRAVERSAL_REFERENCE_ORDER if args.reference_order else capi.TRAVERSAL_AUTO
 
     r = ShardedRenderer(local_rank, rank, world, mode=args.shard, strip_rows=args.strip_rows)
-    r.upload_scene(scene.models, scene.materials, scene.nodes)
+    if args.gpu_bvh:
+        r.ctx.upload_scene_gpu_bvh(scene.models, scene.materials)     # EXPERIMENT: LBVH built on the GPU
+    else:
+        r.upload_scene(scene.models, scene.materials, scene.nodes)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=r.device)   # > 126 MB L2
 
     fp32_peak = None
@@ -247,7 +250,10 @@ def run_ours(args):
         opts = bvr.make_options(W, kernel, traversal)
         win = bvr.make_window(BASE_SEED, H)
         for _ in range(args.steps):
-            r.upload_scene(scene.models, scene.materials, scene.nodes)      # the reference re-uploads every frame
+            if args.gpu_bvh:
+                r.ctx.upload_scene_gpu_bvh(scene.models, scene.materials)
+            else:
+                r.upload_scene(scene.models, scene.materials, scene.nodes)      # the reference re-uploads every frame
             r.ctx.render(cam, 3, win, opts, want=("rgba",), out={"rgba": host_np})   # bvr_render: H2D, kernels, D2H, sync
             e2e_rays += r.ctx.stats()["rays"]
         d2h = host_np.nbytes
@@ -279,6 +285,7 @@ def run_ours(args):
                 "config": {"workload": wl["name"], "scene_seed": SCENE_SEED, "random_seed": BASE_SEED,
                            "spheres": int(len(scene.models)), "kernel": args.kernel,
                            "traversal": "reference-order" if args.reference_order else "near-first",
+                           "bvh": "GPU LBVH" if args.gpu_bvh else "host PLOC (restated obvhs call, extract.rs:316-321)",
                            "sharding": "none" if world == 1 else
                            (f"samples: {wl['spp']} spp per rank, distinct seed per rank, NCCL reduce to rank 0"
                             if args.shard == "samples" else
@@ -362,7 +369,7 @@ def run_c5(args):
     opts = bvr.make_options(W)
     ctx.upload_scene(scene.models, scene.materials, scene.nodes)
     prev_models, prev_nodes = scene.models.copy(), scene.nodes.copy()
-    t_build = t_upload = t_render = 0.0
+    t_build = t_upload = t_render = gpu_build_ms = 0.0
     rays = h2d = 0
     t_all0 = time.perf_counter()
     for f in range(frames):
@@ -370,12 +377,10 @@ def run_c5(args):
         scene.animate(f + 1)                                  # closed-form motion + PLOC rebuild (host)
         t1 = time.perf_counter()
         m, n = scene.models, scene.nodes
-        # dirty ranges: changed models, and the span of changed BVH nodes
+        # dirty model ranges: runs of changed models, bridged over gaps < 16 (one copy per run)
         dm = np.nonzero((m.view(np.uint8).reshape(-1, 32) != prev_models.view(np.uint8).reshape(-1, 32)).any(axis=1))[0]
-        dn = np.nonzero((n.view(np.uint8).reshape(-1, 48) != prev_nodes.view(np.uint8).reshape(-1, 48)).any(axis=1))[0]
         ranges = []
         if len(dm):
-            # runs of consecutive dirty models, bridged over gaps < 16
             start = prev = int(dm[0])
             for i in dm[1:]:
                 i = int(i)
@@ -384,6 +389,25 @@ def run_c5(args):
                     start = i
                 prev = i
             ranges.append((capi.ARRAY_MODELS, start, prev - start + 1))
+        if args.gpu_bvh:
+            # models only travel; the library rebuilds the BVH on the GPU (bvr_upload_scene_gpu_bvh).  The host
+            # PLOC time inside scene.animate() is then not part of the frame: it is subtracted below.
+            st0 = ctx.stats()["h2d_bytes"]
+            ctx.upload_scene_gpu_bvh(m, scene.materials, ranges if f > 0 else None)
+            st1 = ctx.stats()
+            h2d += st1["h2d_bytes"] - st0
+            gpu_build_ms += st1["last_upload_ms"]
+            prev_models = m.copy()
+            t2 = time.perf_counter()
+            ctx.render(cam, 2, bvr.make_window((0.37 + 0.013 * f) % 1.0, H), opts, raster, depth, want=("rgba",), out=out)
+            t3 = time.perf_counter()
+            rays += ctx.stats()["rays"]
+            t_build += t1 - t0
+            t_upload += t2 - t1
+            t_render += t3 - t2
+            continue
+        # ... plus the span of changed BVH nodes
+        dn = np.nonzero((n.view(np.uint8).reshape(-1, 48) != prev_nodes.view(np.uint8).reshape(-1, 48)).any(axis=1))[0]
         if len(dn):
             ranges.append((capi.ARRAY_BVH_NODES, int(dn.min()), int(dn.max() - dn.min() + 1)))
         st0 = ctx.stats()["h2d_bytes"]
@@ -399,6 +423,8 @@ def run_c5(args):
         t_upload += t2 - t1
         t_render += t3 - t2
     total = time.perf_counter() - t_all0
+    if args.gpu_bvh:
+        total -= t_build      # host animate+PLOC is bench scaffolding in this mode (the tree comes from the GPU)
     line = {"metric": "frame ms, animated 10k spheres 1280x720 4spp 4 bounces level 2 (BVH rebuild + dirty upload + render + composite)",
             "value": total / frames * 1e3, "unit": "ms/frame", "n_gpus": 1, "steps": frames, "warmup": 0,
             "ms_per_step": total / frames * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
@@ -407,6 +433,8 @@ def run_c5(args):
                                    "fused depth composite vs synthetic raster"},
             "split_ms": {"host_bvh_build": t_build / frames * 1e3, "dirty_detect_and_upload": t_upload / frames * 1e3,
                          "render_with_host_io": t_render / frames * 1e3},
+            "bvh": "GPU LBVH (bvr_upload_scene_gpu_bvh)" if args.gpu_bvh else "host PLOC (csrc/host/ploc.cpp)",
+            "gpu_upload_and_build_ms": gpu_build_ms / frames if args.gpu_bvh else None,
             "mrays_per_s": rays / total / 1e6, "scene_h2d_bytes_per_frame": h2d / frames,
             "full_scene_bytes": int(scene.models.nbytes + scene.materials.nbytes + scene.nodes.nbytes)}
     print(json.dumps(line), flush=True)
@@ -420,6 +448,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--gpu-bvh", action="store_true", help="c5: build the BVH on the GPU instead of the host PLOC")
     ap.add_argument("--frames", type=int, default=300, help="frames of the animated workload (c5)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "megakernel", "wavefront", "cta-wavefront"])
     ap.add_argument("--reference-order", action="store_true", help="reference traversal order (raytrace.wgsl:313-346)")

@@ -107,6 +107,7 @@ SIGNATURES = {
     "bvr_set_stream": (_i, [_vp, _vp]),
     "bvr_sync": (_i, [_vp]),
     "bvr_upload_scene": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "bvr_upload_scene_gpu_bvh": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
     "bvr_shard_rows": (_u32, [_u32, _P(BvrRenderOptions)]),
     "bvr_render": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _P(BvrWindow), _P(BvrRenderOptions), _vp, _vp, _P(BvrOutputs)]),
     "bvr_render_device": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _P(BvrWindow), _P(BvrRenderOptions), _vp, _vp, _P(BvrOutputs)]),
@@ -145,6 +146,7 @@ SIGNATURES = {
     "bvrh_app_set_window_size": (None, [_vp, _u32, _u32]),
     "bvrh_app_set_seed": (None, [_vp, _f]),
     "bvrh_app_set_render_options": (None, [_vp, _P(BvrRenderOptions)]),
+    "bvrh_app_set_gpu_bvh": (None, [_vp, _i]),
     "bvrh_app_set_raster": (_i, [_vp, _u32, _vp, _vp, _sz]),
     "bvrh_app_update": (_i, [_vp]),
     "bvrh_app_frame": (_vp, [_vp, _u32, _P(_u32), _P(_u32)]),

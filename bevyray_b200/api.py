@@ -167,6 +167,22 @@ class Context:
         self._check(lib.bvr_upload_scene(self._h, _ptr(models), len(models), _ptr(materials), len(materials),
                                          _ptr(nodes), len(nodes), rp, rn))
 
+    def upload_scene_gpu_bvh(self, models, materials, ranges=None, want_nodes=False):
+        """bvr_upload_scene_gpu_bvh: the BVH is built on the GPU; optionally returns the nodes (reference layout)."""
+        models = np.ascontiguousarray(models, dtype=MODEL_DTYPE)
+        materials = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
+        if ranges is None:
+            rp, rn = None, 0
+        else:
+            arr = (capi.BvrDirtyRange * max(len(ranges), 1))()
+            for i, (a, f, c) in enumerate(ranges):
+                arr[i].array, arr[i].first, arr[i].count = a, f, c
+            rp, rn = C.cast(arr, C.c_void_p), len(ranges)
+        nodes = np.zeros(max(2 * len(models) - 1, 0), dtype=BVH_NODE_DTYPE) if want_nodes else None
+        self._check(lib.bvr_upload_scene_gpu_bvh(self._h, _ptr(models), len(models), _ptr(materials), len(materials),
+                                                 rp, rn, _ptr(nodes) if want_nodes and len(nodes) else None))
+        return nodes
+
     def shard_rows(self, height, opts):
         return lib.bvr_shard_rows(height, C.byref(opts))
 

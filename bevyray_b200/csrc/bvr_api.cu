@@ -68,6 +68,8 @@ struct BvrContext {
     int sm_count = 0;
     DeviceBuffer pixel_counter;
     DeviceBuffer wf_state;
+    DeviceBuffer bvh_scratch;
+    unsigned int* depth_host = nullptr;       // pinned
     unsigned int* wf_host_counts = nullptr;   // pinned, 8 words
     PinnedBuffer upload_staging;
     cudaEvent_t upload_done = nullptr;
@@ -222,6 +224,7 @@ int bvr_create(int device, BvrContext** out_ctx) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->ray_counter_host, sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->wf_host_counts, 8 * sizeof(unsigned int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->depth_host, sizeof(unsigned int), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         cudaGetLastError();
         bvr_destroy(ctx);
@@ -240,12 +243,13 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
     if (ctx->ray_counter_host) cudaFreeHost(ctx->ray_counter_host);
     if (ctx->wf_host_counts) cudaFreeHost(ctx->wf_host_counts);
+    if (ctx->depth_host) cudaFreeHost(ctx->depth_host);
     cudaEvent_t evs[] = {ctx->ev_render0, ctx->ev_render1, ctx->ev_upload0, ctx->ev_upload1, ctx->upload_done};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -368,6 +372,98 @@ int bvr_upload_scene(BvrContext* ctx,
     ctx->tree_depth = depth;
     ctx->n_inner = n_inner;
     ctx->has_scene = n_nodes > 0 && n_models > 0;
+    ctx->scene_uploaded = true;
+    return BVR_OK;
+}
+
+int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
+                             const BvrModel* models, size_t n_models,
+                             const BvrMaterial* materials, size_t n_materials,
+                             const BvrDirtyRange* ranges, size_t n_ranges,
+                             BvrBvhNode* out_nodes) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    if ((n_models && !models) || (n_materials && !materials))
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null array with non-zero count");
+    if (n_ranges && !ranges) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null ranges with non-zero count");
+    if (n_models > 0 && n_materials == 0) return fail(ctx, BVR_ERR_BAD_SCENE, "models without materials");
+    if (n_models >= (size_t)BVR_LEAF_FIRST_MASK) return fail(ctx, BVR_ERR_BAD_SCENE, "more than 2^24-1 models");
+    cudaSetDevice(ctx->device);
+    const size_t n_nodes = n_models ? 2 * n_models - 1 : 0;
+    const bool partial = ranges != nullptr && ctx->scene_uploaded && n_models == ctx->n_models &&
+                         n_materials == ctx->n_materials;
+    if (ranges && !partial) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty ranges need a previous upload with the same counts");
+
+    struct Copy { uint32_t array; size_t first, count; };
+    std::vector<Copy> copies;
+    const size_t counts[2] = {n_models, n_materials};
+    if (partial) {
+        for (size_t i = 0; i < n_ranges; i++) {
+            const BvrDirtyRange& r = ranges[i];
+            if (r.array > 1u) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty range: only models / materials may be named");
+            if ((size_t)r.first + r.count > counts[r.array]) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty range out of bounds");
+            if (r.count) copies.push_back({r.array, r.first, r.count});
+        }
+    } else {
+        for (uint32_t a = 0; a < 2; a++) if (counts[a]) copies.push_back({a, 0, counts[a]});
+    }
+    BVR_CK(ctx->raw_models.ensure(n_models * sizeof(BvrModel)));
+    BVR_CK(ctx->raw_materials.ensure(n_materials * sizeof(BvrMaterial)));
+    BVR_CK(ctx->raw_nodes.ensure(n_nodes * sizeof(BvrBvhNode)));
+    BVR_CK(ctx->spheres.ensure(n_models * sizeof(float4)));
+    BVR_CK(ctx->sphere_material.ensure(n_models * sizeof(uint32_t)));
+    BVR_CK(ctx->pairs.ensure(n_nodes * 2 * sizeof(float4)));
+    BVR_CK(ctx->inner_id.ensure(n_nodes * sizeof(uint32_t)));
+    BVR_CK(ctx->block_sums.ensure((n_nodes / 1024 + 2) * sizeof(uint32_t)));
+    BVR_CK(ctx->bvh_scratch.ensure(bvh_build_scratch_bytes((uint32_t)n_models)));
+
+    size_t staging_bytes = 0;
+    for (const Copy& c : copies) staging_bytes += ((c.count * 32) + 255) & ~(size_t)255;
+    if (ctx->upload_pending) { BVR_CK(cudaEventSynchronize(ctx->upload_done)); ctx->upload_pending = false; }
+    BVR_CK(ctx->upload_staging.ensure(staging_bytes));
+    BVR_CK(cudaEventRecord(ctx->ev_upload0, ctx->stream));
+    const void* src_base[2] = {models, materials};
+    void* dst_base[2] = {ctx->raw_models.ptr, ctx->raw_materials.ptr};
+    size_t off = 0;
+    for (const Copy& c : copies) {
+        int st = h2d(ctx, static_cast<char*>(dst_base[c.array]) + c.first * 32,
+                     static_cast<const char*>(src_base[c.array]) + c.first * 32, c.count * 32, ctx->upload_staging, off);
+        if (st != BVR_OK) return st;
+    }
+    BVR_CK(cudaEventRecord(ctx->upload_done, ctx->stream));
+    ctx->upload_pending = true;
+
+    int launches = 0;
+    uint32_t* d_depth = nullptr;
+    *ctx->depth_host = 0;
+    if (n_models) {
+        const int nb = launch_bvh_build(ctx->raw_models.as<RawModel>(), (uint32_t)n_models, ctx->raw_nodes.as<RawNode>(),
+                                        ctx->bvh_scratch.ptr, &d_depth, ctx->stream);
+        if (nb < 0) return fail_cuda(ctx, cudaGetLastError(), "GPU BVH build");
+        launches += nb;
+        launches += launch_derive_spheres(ctx->raw_models.as<RawModel>(), (uint32_t)n_models, ctx->spheres.as<float4>(),
+                                          ctx->sphere_material.as<uint32_t>(), ctx->stream);
+        launches += launch_derive_pairs(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+                                        ctx->block_sums.as<uint32_t>(), ctx->pairs.as<float4>(), ctx->root_ref.as<uint32_t>(),
+                                        ctx->stream);
+        BVR_CK(cudaMemcpyAsync(ctx->depth_host, d_depth, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_nodes) {
+            BVR_CK(cudaMemcpyAsync(out_nodes, ctx->raw_nodes.ptr, n_nodes * sizeof(BvrBvhNode), cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->stats.d2h_bytes += n_nodes * sizeof(BvrBvhNode);
+        }
+    }
+    BVR_CK(cudaGetLastError());
+    BVR_CK(cudaEventRecord(ctx->ev_upload1, ctx->stream));
+    BVR_CK(cudaStreamSynchronize(ctx->stream));   // the stack bound (tree depth) is needed on the host
+    ctx->upload_timed = true;
+    ctx->stats.kernel_launches += (uint64_t)launches;
+    ctx->n_models = n_models;
+    ctx->n_materials = n_materials;
+    ctx->n_nodes = n_nodes;
+    ctx->tree_depth = *ctx->depth_host;
+    ctx->n_inner = n_models ? (uint32_t)(n_models - 1) : 0u;
+    ctx->root_ref_host = (n_models == 1) ? (BVR_LEAF_BIT | 0u) : 0u;
+    ctx->has_scene = n_models > 0;
     ctx->scene_uploaded = true;
     return BVR_OK;
 }

@@ -248,9 +248,11 @@ struct SphereQueryItem {
 
 // prepare_buffers — extract.rs:280-337.  Throws std::runtime_error("This should exist") when a
 // material handle has no prepared asset (the reference panics, extract.rs:302).
+// build_bvh == false leaves the BVH buffer untouched (the library builds the tree on the GPU instead,
+// RayTracingNode::gpu_bvh).
 void prepare_buffers(ModelBuffer& model_buffer, MaterialBuffer& material_buffer, BVHBuffer& bvh_buffer,
                      const std::vector<SphereQueryItem>& data,
-                     const std::vector<std::optional<BvrMaterial>>& render_assets);
+                     const std::vector<std::optional<BvrMaterial>>& render_assets, bool build_bvh = true);
 
 // ------------------------------------------------------------------------------------------------
 // Render graph node + pipeline (src/raytracing/pipeline.rs)
@@ -292,6 +294,7 @@ private:
 // storage buffer -> no binding).  Throws std::runtime_error on a C-ABI error.
 struct RayTracingNode {
     BvrRenderOptions options{};   // kernel / traversal / sharding knobs the reference does not have
+    bool gpu_bvh = false;         // build the BVH on the GPU (bvr_upload_scene_gpu_bvh) instead of uploading the host tree
     bool run(RaytracingPipeline& pipeline, ViewTarget& view_target, const ViewPrepassTextures& prepass,
              const BvrRaytraceLevel& level, const BvrCamera& camera, const WindowExtract& window,
              ModelBuffer& model, MaterialBuffer& material, BVHBuffer& bvh) const;

@@ -214,6 +214,10 @@ void bvrh_app_set_render_options(BvrhApp* app, const BvrRenderOptions* opts) {
     if (app && opts) app->app.render.node.options = *opts;
 }
 
+void bvrh_app_set_gpu_bvh(BvrhApp* app, int enabled) {
+    if (app) app->app.render.node.gpu_bvh = enabled != 0;
+}
+
 int bvrh_app_set_raster(BvrhApp* app, uint32_t camera, const float* rgba, const float* depth, size_t n_pixels) {
     if (!app || !rgba || !depth) return 1;
     app->app.set_raster(camera, std::vector<float>(rgba, rgba + 4 * n_pixels), std::vector<float>(depth, depth + n_pixels));

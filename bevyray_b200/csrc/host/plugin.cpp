@@ -169,7 +169,7 @@ template class StorageBuffer<BvrBvhNode>;
 
 void prepare_buffers(ModelBuffer& model_buffer, MaterialBuffer& material_buffer, BVHBuffer& bvh_buffer,
                      const std::vector<SphereQueryItem>& data,
-                     const std::vector<std::optional<BvrMaterial>>& render_assets) {
+                     const std::vector<std::optional<BvrMaterial>>& render_assets, bool build_bvh) {
     // `let Ok(..) = buffer.lock() else { return }` (extract.rs:287-297): lock() blocks and only fails on a
     // poisoned mutex, which std::mutex cannot be.
     std::lock_guard<std::mutex> l0(model_buffer.mutex), l1(material_buffer.mutex), l2(bvh_buffer.mutex);
@@ -192,10 +192,9 @@ void prepare_buffers(ModelBuffer& model_buffer, MaterialBuffer& material_buffer,
         m.material_id = index++;
         all_spheres.push_back(m);
     }
-    std::vector<BvrBvhNode> bvh_nodes = build_ploc(all_spheres, 24);
+    if (build_bvh) bvh_buffer.buffer.set(build_ploc(all_spheres, 24));
     model_buffer.buffer.set(std::move(all_spheres));
     material_buffer.buffer.set(std::move(all_materials));
-    bvh_buffer.buffer.set(std::move(bvh_nodes));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -247,7 +246,7 @@ bool RayTracingNode::run(RaytracingPipeline& pipeline, ViewTarget& view_target, 
     const auto& materials = material.buffer.get();
     const auto& nodes = bvh.buffer.get();
     // an empty storage buffer has no binding -> the reference returns early (pipeline.rs:141-151)
-    if (models.empty() || materials.empty() || nodes.empty()) return false;
+    if (models.empty() || materials.empty() || (nodes.empty() && !gpu_bvh)) return false;
 
     BvrContext* ctx = pipeline.context();
     // pipeline.rs:136-138: three write_buffer calls; here only the dirty element ranges travel
@@ -255,11 +254,14 @@ bool RayTracingNode::run(RaytracingPipeline& pipeline, ViewTarget& view_target, 
     bool full = false;
     append_ranges(ranges, BVR_ARRAY_MODELS, model.buffer, full);
     append_ranges(ranges, BVR_ARRAY_MATERIALS, material.buffer, full);
-    append_ranges(ranges, BVR_ARRAY_BVH_NODES, bvh.buffer, full);
+    if (!gpu_bvh) append_ranges(ranges, BVR_ARRAY_BVH_NODES, bvh.buffer, full);
     if (full || !ranges.empty()) {
-        int st = bvr_upload_scene(ctx, models.data(), models.size(), materials.data(), materials.size(),
-                                  nodes.data(), nodes.size(), full ? nullptr : ranges.data(),
-                                  full ? 0 : ranges.size());
+        int st = gpu_bvh
+                     ? bvr_upload_scene_gpu_bvh(ctx, models.data(), models.size(), materials.data(), materials.size(),
+                                                full ? nullptr : ranges.data(), full ? 0 : ranges.size(), nullptr)
+                     : bvr_upload_scene(ctx, models.data(), models.size(), materials.data(), materials.size(),
+                                        nodes.data(), nodes.size(), full ? nullptr : ranges.data(),
+                                        full ? 0 : ranges.size());
         if (st != BVR_OK) throw std::runtime_error(std::string("bvr_upload_scene: ") + bvr_last_error(ctx));
     }
     BvrRenderOptions opts = options;
@@ -381,7 +383,7 @@ int App::update() {
     if (!plugin_added_) return 0;
     // RenderSet::PrepareResources, extract.rs:50
     prepare_buffers(render.model_buffer, render.material_buffer, render.bvh_buffer, render.spheres,
-                    render.render_assets);
+                    render.render_assets, !render.node.gpu_bvh);
     // Core3d graph: Tonemapping -> RaytraceLabel -> EndMainPassPostProcessing, one run per view
     int rendered = 0;
     if (!render.has_raytrace_node || !render.window) return 0;

@@ -70,6 +70,11 @@ int launch_derive_spheres(const RawModel* models, uint32_t n, float4* spheres, u
 int launch_derive_pairs(const RawNode* nodes, uint32_t n_nodes, uint32_t* inner_id, uint32_t* block_sums,
                         float4* pairs, uint32_t* root_ref_out, cudaStream_t stream);
 
+// ---- GPU BVH builder (bvh_build.cu) ----
+size_t bvh_build_scratch_bytes(uint32_t n_models);
+int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, void* scratch, uint32_t** depth_out,
+                     cudaStream_t stream);
+
 // ---- render kernels ----
 int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple one-thread-per-pixel kernel (v1)
 // persistent-lane megakernel; returns -1 when the configuration does not fit (caller falls back to v1)

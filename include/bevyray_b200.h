@@ -218,6 +218,16 @@ int bvr_upload_scene(BvrContext* ctx,
                      const BvrBvhNode* nodes, size_t n_nodes,
                      const BvrDirtyRange* ranges, size_t n_ranges);
 
+/* Same as bvr_upload_scene, but the BVH is BUILT ON THE GPU from the models (LBVH emitting the BVHNode
+ * contract) instead of being supplied: replaces obvhs::ploc::build_ploc + the node mapping at
+ * src/raytracing/extract.rs:316-332 for callers that opt in.  `ranges` may name models / materials only.
+ * `out_nodes` (nullable) receives the 2*n_models-1 nodes in the reference layout. */
+int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
+                             const BvrModel* models, size_t n_models,
+                             const BvrMaterial* materials, size_t n_materials,
+                             const BvrDirtyRange* ranges, size_t n_ranges,
+                             BvrBvhNode* out_nodes);
+
 /* Rows this shard renders for an image of `height` rows (== height when unsharded). */
 uint32_t bvr_shard_rows(uint32_t height, const BvrRenderOptions* opts);
 

@@ -81,6 +81,8 @@ void     bvrh_app_set_window_size(BvrhApp* app, uint32_t physical_width, uint32_
 /* fixed value for WindowExtract.random_seed (extract.rs:72-73 draws a random one); negative = random again */
 void     bvrh_app_set_seed(BvrhApp* app, float seed);
 void     bvrh_app_set_render_options(BvrhApp* app, const BvrRenderOptions* opts);
+/* non-zero: skip the host PLOC build in prepare_buffers and let the library build the BVH on the GPU */
+void     bvrh_app_set_gpu_bvh(BvrhApp* app, int enabled);
 int      bvrh_app_set_raster(BvrhApp* app, uint32_t camera, const float* rgba, const float* depth, size_t n_pixels);
 /* One frame.  Returns the number of views rendered (0 = skipped like the reference's early returns), -1 on error. */
 int      bvrh_app_update(BvrhApp* app);
