@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Small render through every kernel variant, meant to run under compute-sanitizer
+(memcheck / racecheck / synccheck):  compute-sanitizer --tool racecheck python tools/sanitize_small.py"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bevyray_b200 as bvr  # noqa: E402
+
+scene = bvr.Scene.rtiow(1)
+W, H = 64, 36
+cam = bvr.make_camera(position=(13, 2, 3), target=(0, 0, 0), fov=float(np.deg2rad(20)), aspect=W / H, sample_count=2, bounces=4)
+win = bvr.make_window(0.37, H)
+ctx = bvr.Context(0)
+ctx.upload_scene(scene.models, scene.materials, scene.nodes)
+ref = None
+for kernel, traversal, name in [(1, 0, "megakernel"), (1, 1, "reference-order"), (2, 0, "wavefront"), (3, 0, "cta-wavefront")]:
+    out = ctx.render(cam, 3, win, bvr.make_options(W, kernel=kernel, traversal=traversal))
+    if ref is None:
+        ref = out
+    same = all(np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)) for k in ref)
+    print(name, "rays", ctx.stats()["rays"], "identical" if same else "DIFFERENT")
+nodes = ctx.upload_scene_gpu_bvh(scene.models, scene.materials, want_nodes=True)
+out = ctx.render(cam, 3, win, bvr.make_options(W))
+print("gpu-bvh", bvr.validate_bvh(nodes, scene.models), all(np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)) for k in ref))
+big = bvr.Scene.random(7, 3000, 30.0, 0.05, 0.25)
+ctx.upload_scene(big.models, big.materials, big.nodes)
+ctx.render(cam, 3, win, bvr.make_options(W))
+print("done")
