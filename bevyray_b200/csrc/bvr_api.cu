@@ -58,7 +58,7 @@ struct BvrContext {
 
     // scene, reference layout (raw bytes in HBM) and the derived traversal layout
     DeviceBuffer raw_models, raw_materials, raw_nodes;
-    DeviceBuffer spheres, sphere_material, pairs, inner_id, block_sums, root_ref;
+    DeviceBuffer spheres, sphere_material, pairs, pairs_ch, inner_id, block_sums, root_ref;
     size_t n_models = 0, n_materials = 0, n_nodes = 0;
     bool scene_uploaded = false;
     bool has_scene = false;
@@ -241,7 +241,7 @@ void bvr_destroy(BvrContext* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
-                            &ctx->sphere_material, &ctx->pairs, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
+                            &ctx->sphere_material, &ctx->pairs, &ctx->pairs_ch, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
                             &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch};
     for (DeviceBuffer* b : bufs) b->release();
@@ -320,6 +320,7 @@ int bvr_upload_scene(BvrContext* ctx,
     BVR_CK(ctx->spheres.ensure(n_models * sizeof(float4)));
     BVR_CK(ctx->sphere_material.ensure(n_models * sizeof(uint32_t)));
     BVR_CK(ctx->pairs.ensure(n_nodes * 2 * sizeof(float4)));   // <= ceil(n/2) inner nodes x 64 B
+    BVR_CK(ctx->pairs_ch.ensure(n_nodes * 2 * sizeof(float4)));
     BVR_CK(ctx->inner_id.ensure(n_nodes * sizeof(uint32_t)));
     BVR_CK(ctx->block_sums.ensure((n_nodes / 1024 + 2) * sizeof(uint32_t)));
 
@@ -352,7 +353,7 @@ int bvr_upload_scene(BvrContext* ctx,
                                           ctx->spheres.as<float4>(), ctx->sphere_material.as<uint32_t>(), ctx->stream);
     if (nodes_dirty || !partial) {
         launches += launch_derive_pairs(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
-                                        ctx->block_sums.as<uint32_t>(), ctx->pairs.as<float4>(),
+                                        ctx->block_sums.as<uint32_t>(), ctx->pairs.as<float4>(), ctx->pairs_ch.as<float4>(),
                                         ctx->root_ref.as<uint32_t>(), ctx->stream);
         // root ref on the host (needed as a kernel parameter): a leaf root is encoded like any leaf ref
         if (n_nodes) {
@@ -413,6 +414,7 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
     BVR_CK(ctx->spheres.ensure(n_models * sizeof(float4)));
     BVR_CK(ctx->sphere_material.ensure(n_models * sizeof(uint32_t)));
     BVR_CK(ctx->pairs.ensure(n_nodes * 2 * sizeof(float4)));
+    BVR_CK(ctx->pairs_ch.ensure(n_nodes * 2 * sizeof(float4)));
     BVR_CK(ctx->inner_id.ensure(n_nodes * sizeof(uint32_t)));
     BVR_CK(ctx->block_sums.ensure((n_nodes / 1024 + 2) * sizeof(uint32_t)));
     BVR_CK(ctx->bvh_scratch.ensure(bvh_build_scratch_bytes((uint32_t)n_models)));
@@ -444,8 +446,8 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
         launches += launch_derive_spheres(ctx->raw_models.as<RawModel>(), (uint32_t)n_models, ctx->spheres.as<float4>(),
                                           ctx->sphere_material.as<uint32_t>(), ctx->stream);
         launches += launch_derive_pairs(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
-                                        ctx->block_sums.as<uint32_t>(), ctx->pairs.as<float4>(), ctx->root_ref.as<uint32_t>(),
-                                        ctx->stream);
+                                        ctx->block_sums.as<uint32_t>(), ctx->pairs.as<float4>(), ctx->pairs_ch.as<float4>(),
+                                        ctx->root_ref.as<uint32_t>(), ctx->stream);
         BVR_CK(cudaMemcpyAsync(ctx->depth_host, d_depth, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         if (out_nodes) {
             BVR_CK(cudaMemcpyAsync(out_nodes, ctx->raw_nodes.ptr, n_nodes * sizeof(BvrBvhNode), cudaMemcpyDeviceToHost, ctx->stream));
@@ -485,6 +487,7 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     RenderParams p;
     std::memset(&p, 0, sizeof p);
     p.scene.pairs = ctx->pairs.as<float4>();
+    p.scene.pairs_ch = ctx->pairs_ch.as<float4>();
     p.scene.spheres = ctx->spheres.as<float4>();
     p.scene.sphere_material = ctx->sphere_material.as<uint32_t>();
     p.scene.materials = ctx->raw_materials.as<float4>();

@@ -31,13 +31,13 @@ __global__ void __launch_bounds__(THREADS) cta_wavefront_kernel(const WavefrontP
     if (SMEM_SCENE) {
         float4* sm_pairs = sm_cursor;   sm_cursor += 4u * n_inner;
         float4* sm_spheres = sm_cursor; sm_cursor += n_models;
-        for (uint32_t i = tid; i < 4u * n_inner; i += THREADS) sm_pairs[i] = w.r.scene.pairs[i];
+        for (uint32_t i = tid; i < 4u * n_inner; i += THREADS) sm_pairs[i] = w.r.scene.pairs_ch[i];
         for (uint32_t i = tid; i < n_models; i += THREADS) sm_spheres[i] = w.r.scene.spheres[i];
-        sv.pairs = sm_pairs;
+        sv.pairs_ch = sm_pairs;
         sv.spheres = sm_spheres;
     }
     const uint32_t s_stack0 = wf_smem_addr(sm_cursor) + tid * 8u;
-    const uint32_t s_pairs = SMEM_SCENE ? wf_smem_addr(sv.pairs) : 0u;
+    const uint32_t s_pairs = SMEM_SCENE ? wf_smem_addr(sv.pairs_ch) : 0u;
 
     // this CTA's slice of the slot-indexed arrays and queues
     const uint32_t slot0 = blockIdx.x * CW_POOL;

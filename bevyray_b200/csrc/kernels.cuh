@@ -68,7 +68,7 @@ int launch_derive_spheres(const RawModel* models, uint32_t n, float4* spheres, u
                           cudaStream_t stream);
 // inner_id: scratch of n_nodes u32; block_sums: scratch of ceil(n_nodes/1024)+1 u32
 int launch_derive_pairs(const RawNode* nodes, uint32_t n_nodes, uint32_t* inner_id, uint32_t* block_sums,
-                        float4* pairs, uint32_t* root_ref_out, cudaStream_t stream);
+                        float4* pairs, float4* pairs_ch, uint32_t* root_ref_out, cudaStream_t stream);
 
 // ---- GPU BVH builder (bvh_build.cu) ----
 size_t bvh_build_scratch_bytes(uint32_t n_models);

@@ -96,7 +96,7 @@ __device__ __forceinline__ uint32_t make_ref(const RawNode& child, uint32_t chil
 // pass 4: one 64-byte child-pair record per inner node
 __global__ void build_pairs_kernel(const RawNode* __restrict__ nodes, uint32_t n,
                                    const uint32_t* __restrict__ inner_id, float4* __restrict__ pairs,
-                                   uint32_t* __restrict__ root_ref_out) {
+                                   float4* __restrict__ pairs_ch, uint32_t* __restrict__ root_ref_out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const RawNode nd = nodes[i];
@@ -110,6 +110,21 @@ __global__ void build_pairs_kernel(const RawNode* __restrict__ nodes, uint32_t n
     out[1] = make_float4(c0.mx[1], c0.mx[2], c1.mn[0], c1.mn[1]);
     out[2] = make_float4(c1.mn[2], c1.mx[0], c1.mx[1], c1.mx[2]);
     out[3] = make_float4(__uint_as_float(r0), __uint_as_float(r1), 0.0f, 0.0f);
+    // centre / half-extent form for the culling-only slab test: the half extents are rounded UP, so that
+    // [c - h, c + h] encloses [min, max] exactly — the box can only grow
+    float c[2][3], h[2][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        c[0][k] = __fmul_rn(0.5f, __fadd_rn(c0.mn[k], c0.mx[k]));
+        h[0][k] = fmaxf(__fsub_ru(c0.mx[k], c[0][k]), __fsub_ru(c[0][k], c0.mn[k]));
+        c[1][k] = __fmul_rn(0.5f, __fadd_rn(c1.mn[k], c1.mx[k]));
+        h[1][k] = fmaxf(__fsub_ru(c1.mx[k], c[1][k]), __fsub_ru(c[1][k], c1.mn[k]));
+    }
+    float4* och = pairs_ch + 4u * inner_id[i];
+    och[0] = make_float4(c[0][0], c[0][1], c[0][2], h[0][0]);
+    och[1] = make_float4(h[0][1], h[0][2], c[1][0], c[1][1]);
+    och[2] = make_float4(c[1][2], h[1][0], h[1][1], h[1][2]);
+    och[3] = out[3];
 }
 
 }  // namespace
@@ -122,13 +137,13 @@ int launch_derive_spheres(const RawModel* models, uint32_t n, float4* spheres, u
 }
 
 int launch_derive_pairs(const RawNode* nodes, uint32_t n_nodes, uint32_t* inner_id, uint32_t* block_sums,
-                        float4* pairs, uint32_t* root_ref_out, cudaStream_t stream) {
+                        float4* pairs, float4* pairs_ch, uint32_t* root_ref_out, cudaStream_t stream) {
     if (n_nodes == 0) return 0;
     const uint32_t n_blocks = (n_nodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
     count_inner_kernel<<<n_blocks, SCAN_BLOCK, 0, stream>>>(nodes, n_nodes, block_sums);
     scan_block_sums_kernel<<<1, SCAN_BLOCK, 0, stream>>>(block_sums, n_blocks);
     assign_inner_id_kernel<<<n_blocks, SCAN_BLOCK, 0, stream>>>(nodes, n_nodes, block_sums, inner_id);
-    build_pairs_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(nodes, n_nodes, inner_id, pairs, root_ref_out);
+    build_pairs_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(nodes, n_nodes, inner_id, pairs, pairs_ch, root_ref_out);
     return 4;
 }
 

@@ -27,7 +27,9 @@ namespace bvr {
 #define BVR_FAST_STACK 64
 
 struct SceneView {
-    const float4* __restrict__ pairs;            // 4 x float4 per inner node
+    const float4* __restrict__ pairs;            // 4 x float4 per inner node: child boxes as (min, max)
+    const float4* __restrict__ pairs_ch;         // same records with the boxes as (centre, half extent):
+                                                 //   q0 = (c0.xyz, h0.x) q1 = (h0.yz, c1.xy) q2 = (c1.z, h1.xyz) q3 = refs
     const float4* __restrict__ spheres;          // (centre.xyz, radius) per model
     const uint32_t* __restrict__ sphere_material;  // Model::material_id per model
     const float4* __restrict__ materials;        // 2 x float4 per material (reference bytes)

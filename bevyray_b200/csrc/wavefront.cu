@@ -54,14 +54,14 @@ __global__ void __launch_bounds__(WF_THREADS) wf_extend(const WavefrontParams w,
     if (SMEM_SCENE) {
         float4* sm_pairs = sm_cursor;   sm_cursor += 4u * n_inner;
         float4* sm_spheres = sm_cursor; sm_cursor += n_models;
-        for (uint32_t i = tid; i < 4u * n_inner; i += WF_THREADS) sm_pairs[i] = w.r.scene.pairs[i];
+        for (uint32_t i = tid; i < 4u * n_inner; i += WF_THREADS) sm_pairs[i] = w.r.scene.pairs_ch[i];
         for (uint32_t i = tid; i < n_models; i += WF_THREADS) sm_spheres[i] = w.r.scene.spheres[i];
-        sv.pairs = sm_pairs;
+        sv.pairs_ch = sm_pairs;
         sv.spheres = sm_spheres;
         __syncthreads();
     }
     const uint32_t s_stack0 = wf_smem_addr(sm_cursor) + tid * 8u;
-    const uint32_t s_pairs = SMEM_SCENE ? wf_smem_addr(sv.pairs) : 0u;
+    const uint32_t s_pairs = SMEM_SCENE ? wf_smem_addr(sv.pairs_ch) : 0u;
     const unsigned long long rays = wf_stage_extend<WF_THREADS * 8u, SMEM_SCENE>(w, sv, q_ray_in, n_rays, w.counters + WC_HEAD,
                                                                                 s_stack0, s_pairs, tune);
     unsigned long long sum = rays;

@@ -194,14 +194,14 @@ __device__ __forceinline__ void wf_sts64(uint32_t addr, uint32_t a, uint32_t b) 
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
-// culling-only slab test (see megakernel_v3.cu::box_cull)
-__device__ __forceinline__ bool wf_box_cull(V3 inv, V3 noi, float closest_t, float mnx, float mny, float mnz, float mxx,
-                                            float mxy, float mxz, float& entry) {
-    const float t0x = __fmaf_rn(mnx, inv.x, noi.x), t1x = __fmaf_rn(mxx, inv.x, noi.x);
-    const float t0y = __fmaf_rn(mny, inv.y, noi.y), t1y = __fmaf_rn(mxy, inv.y, noi.y);
-    const float t0z = __fmaf_rn(mnz, inv.z, noi.z), t1z = __fmaf_rn(mxz, inv.z, noi.z);
-    entry = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
-    const float exit = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), closest_t));
+// culling-only slab test on (centre, half extent) boxes (see megakernel_v3.cu::box_cull)
+__device__ __forceinline__ bool wf_box_cull(V3 inv, V3 noi, float closest_t, float cx, float cy, float cz, float hx,
+                                            float hy, float hz, float& entry) {
+    const float tcx = __fmaf_rn(cx, inv.x, noi.x), thx = hx * fabsf(inv.x);
+    const float tcy = __fmaf_rn(cy, inv.y, noi.y), thy = hy * fabsf(inv.y);
+    const float tcz = __fmaf_rn(cz, inv.z, noi.z), thz = hz * fabsf(inv.z);
+    entry = fmaxf(fmaxf(tcx - thx, tcy - thy), fmaxf(tcz - thz, 0.0f));
+    const float exit = fminf(fminf(tcx + thx, tcy + thy), fminf(tcz + thz, closest_t));
     return entry <= exit;
 }
 
@@ -278,7 +278,7 @@ __device__ __forceinline__ unsigned long long wf_stage_extend(const WavefrontPar
                             const uint2 rr = wf_lds64(na + 48u);
                             r0 = rr.x; r1 = rr.y;
                         } else {
-                            const float4* nd = sv.pairs + 4u * c;
+                            const float4* nd = sv.pairs_ch + 4u * c;
                             q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2);
                             const float4 q3 = __ldg(nd + 3);
                             r0 = __float_as_uint(q3.x); r1 = __float_as_uint(q3.y);
