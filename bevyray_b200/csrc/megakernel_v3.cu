@@ -27,6 +27,9 @@ enum LaneState : int { NEED_PIXEL = 0, NEW_PATH = 1, RAY_READY = 2, TRAVERSE = 3
 enum Kind : int { K_NONE = 0, K_MISS = 1, K_METAL = 2, K_GLASS = 3, K_DIFFUSE = 4 };
 
 #define V3_NONE 0x7fffffffu
+#ifndef BVR_STEPS_PER_VOTE
+#define BVR_STEPS_PER_VOTE 2   // traversal steps between two rounds of warp votes
+#endif
 
 // Explicit 32-bit shared-window addressing: keeps the per-step address math at one IMAD instead of the
 // generic-to-shared conversion the compiler re-derives every time (ncu r01_v3a: 18 instructions per push).
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         for (;;) {
             bool blocked = false;
 #pragma unroll
-            for (int rep = 0; rep < 2; rep++) {
+            for (int rep = 0; rep < BVR_STEPS_PER_VOTE; rep++) {
                 if (state == TRAVERSE) {
                     uint32_t c = cur;
                     if (c < V3_NONE) {                       // inner node: test both children
