@@ -113,8 +113,17 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_sample(bvr, oracle, scene, wl, spp, threads=0):
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample(bvr, oracle, scene, wl, spp, threads=None):
     """Times the CPU oracle on a bounded sample of the workload: the same frame at `spp` samples."""
+    threads = host_threads() if threads is None else threads
     cam = make_cam(bvr, wl, spp)
     win = bvr.make_window(BASE_SEED, wl["height"])
     t0 = time.perf_counter()
@@ -135,7 +144,7 @@ def run_reference(args):
     wl = WORKLOADS[args.workload]
     scene = make_scene(bvr, wl)
     sample_spp = max(1, min(wl["spp"], args.cpu_spp))
-    cores = oracle.max_threads()
+    cores = host_threads()
     for _ in range(args.warmup):
         cpu_sample(bvr, oracle, scene, dict(wl, width=wl["width"] // 4, height=wl["height"] // 4), 1)
     rays, total = 0, 0.0
@@ -302,7 +311,7 @@ def run_ours(args):
             from oracle import oracle
             sample_spp = max(1, min(wl["spp"], args.cpu_spp))
             cnt, dt = cpu_sample(bvr, oracle, scene, wl, sample_spp)
-            line["cpu_baseline"] = {"value": cnt["rays"] / dt / 1e6, "unit": UNIT, "cores": oracle.max_threads(),
+            line["cpu_baseline"] = {"value": cnt["rays"] / dt / 1e6, "unit": UNIT, "cores": host_threads(),
                                     "kind": "port",
                                     "sample": f"{W}x{H} x {sample_spp} spp of {wl['spp']} (same scene, camera, seed, bounces); "
                                               "restated C++ CPU baseline, not lavapipe"}
