@@ -20,6 +20,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/s, RTIOW final scene 1920x1080 100 spp 10 bounces (ray = one raycast() call, raytrace.wgsl:190)"
+METRIC_C3 = "Mrays/s, RTIOW final scene 3840x2160 1000 spp 10 bounces (ray = one raycast() call)"
 METRIC_C4 = "Mrays/s, synthetic 2^20 random spheres 1920x1080 64 spp 10 bounces (ray = one raycast() call)"
 UNIT = "Mrays/s"
 SCENE_SEED = 1
@@ -33,6 +34,10 @@ WORKLOADS = {
     "c4": dict(name="C4 synthetic 2^20 random spheres (cube side 200, r in [0.05,0.25], 80/15/5 % materials), "
                     "1920x1080 64spp 10 bounces, camera (0,0,130)->(0,0,0) fov pi/4",
                width=1920, height=1080, spp=64, bounces=10, camera="c4", scene=("random", 7, 1 << 20, 200.0, 0.05, 0.25)),
+    # BASELINE.json configs[2]: 4K, 1000 spp, tile- or sample-sharded over the GPUs of the box (strong scaling: with
+    # --shard samples every rank renders 1000/N samples of the whole frame with its own seed)
+    "c3": dict(name="C3 rtiow-final 3840x2160 1000spp 10 bounces, book camera (13,2,3)->(0,0,0) vfov 20deg",
+               width=3840, height=2160, spp=1000, bounces=10, camera="book", split_spp=True),
     # BASELINE.json configs[0] (plumbing / parity case)
     "c1": dict(name="C1 default scene 1280x720 1spp 4 bounces, repo camera (0,0,5)->(0,0,0) fov pi/4",
                width=1280, height=720, spp=1, bounces=4, camera="repo"),
@@ -154,7 +159,7 @@ def run_reference(args):
         total += dt
     value = rays / total / 1e6
     sample = f"{wl['width']}x{wl['height']} x {sample_spp} spp of {wl['spp']} per step (same scene, camera, seed, bounces)"
-    line = {"impl": "reference", "metric": METRIC_C4 if args.workload == "c4" else METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": {"c4": METRIC_C4, "c3": METRIC_C3}.get(args.workload, METRIC), "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3 * (wl["spp"] / sample_spp),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "l2": "not applicable (CPU)",
@@ -185,7 +190,9 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     W, H = wl["width"], wl["height"]
     scene = make_scene(bvr, wl)
-    cam = make_cam(bvr, wl)
+    split_spp = bool(wl.get("split_spp")) and args.shard == "samples" and world > 1
+    rank_spp = max(1, wl["spp"] // world) if split_spp else wl["spp"]
+    cam = make_cam(bvr, wl, rank_spp)
     kernel = {"auto": capi.KERNEL_AUTO, "megakernel": capi.KERNEL_MEGAKERNEL, "wavefront": capi.KERNEL_WAVEFRONT,
               "cta-wavefront": capi.KERNEL_CTA_WAVEFRONT}[args.kernel]
     traversal = capi.TRAVERSAL_REFERENCE_ORDER if args.reference_order else capi.TRAVERSAL_AUTO
@@ -287,20 +294,20 @@ def run_ours(args):
     e2e_value = e2e_rays / e2e_s / 1e6
 
     if rank == 0:
-        line = {"metric": METRIC_C4 if args.workload == "c4" else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": {"c4": METRIC_C4, "c3": METRIC_C3}.get(args.workload, METRIC), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak" if args.shard == "samples" else "strong", "vs_baseline": None, "dtype": "f32",
+                "scaling": "weak" if (args.shard == "samples" and not split_spp) else "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "scene_seed": SCENE_SEED, "random_seed": BASE_SEED,
                            "spheres": int(len(scene.models)), "kernel": args.kernel,
                            "traversal": "reference-order" if args.reference_order else "near-first",
                            "bvh": "GPU LBVH" if args.gpu_bvh else "host PLOC (restated obvhs call, extract.rs:316-321)",
                            "sharding": "none" if world == 1 else
-                           (f"samples: {wl['spp']} spp per rank, distinct seed per rank, NCCL reduce to rank 0"
+                           (f"samples: {rank_spp} spp per rank, distinct seed per rank, NCCL reduce to rank 0"
                             if args.shard == "samples" else
                             f"tiles: {args.strip_rows}-row strips interleaved over ranks, NCCL all_gather"),
                            "l2": "256 MiB buffer written between timed steps (L2 flush)"},
-                "frame_ms": total_ms / args.steps, "mpaths_per_s": W * H * wl["spp"] * world * args.steps / (total_ms * 1e-3) / 1e6
+                "frame_ms": total_ms / args.steps, "mpaths_per_s": W * H * rank_spp * world * args.steps / (total_ms * 1e-3) / 1e6
                 if args.shard == "samples" else W * H * wl["spp"] * args.steps / (total_ms * 1e-3) / 1e6,
                 "rays_per_step": rays // args.steps, "wall_s_timed_region": t_wall,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes) * world,

@@ -65,6 +65,7 @@ struct BvrContext {
     uint32_t root_ref_host = 0;
     uint32_t tree_depth = 0;
     uint32_t n_inner = 0;
+    uint32_t max_leaf_models = 0;
     int sm_count = 0;
     DeviceBuffer pixel_counter;
     DeviceBuffer wf_state;
@@ -132,10 +133,12 @@ uint32_t shard_rows_impl(uint32_t height, const BvrRenderOptions* o) {
 // (raytrace.wgsl:80-87, 313-346): everything reachable from node 0 exactly once, indices in range.
 // Also yields the tree depth (stack bound for the near-first traversal).
 int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, size_t n_materials,
-                   const BvrBvhNode* nodes, size_t n_nodes, uint32_t* depth_out, uint32_t* n_inner_out) {
+                   const BvrBvhNode* nodes, size_t n_nodes, uint32_t* depth_out, uint32_t* n_inner_out,
+                   uint32_t* max_leaf_out) {
     (void)models;
     *depth_out = 0;
     *n_inner_out = 0;
+    *max_leaf_out = 0;
     if (n_models > 0 && n_materials == 0) return fail(ctx, BVR_ERR_BAD_SCENE, "models without materials");
     if (n_models >= (size_t)BVR_LEAF_FIRST_MASK) return fail(ctx, BVR_ERR_BAD_SCENE, "more than 2^24-1 models");
     if (n_nodes == 0) return BVR_OK;
@@ -153,6 +156,7 @@ int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, siz
         if (nd.model_count > 0) {
             if (nd.model_count > BVR_MAX_LEAF_COUNT) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf with more than 128 models");
             if ((size_t)nd.index + nd.model_count > n_models) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf model range out of bounds");
+            if (nd.model_count > *max_leaf_out) *max_leaf_out = nd.model_count;
         } else {
             (*n_inner_out)++;
             if ((size_t)nd.index + 1 >= n_nodes) return fail(ctx, BVR_ERR_BAD_SCENE, "child index out of bounds");
@@ -293,8 +297,8 @@ int bvr_upload_scene(BvrContext* ctx,
     if (ranges && !ctx->scene_uploaded)
         return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty ranges given before any full upload");
 
-    uint32_t depth = 0, n_inner = 0;
-    int st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth, &n_inner);
+    uint32_t depth = 0, n_inner = 0, max_leaf = 0;
+    int st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth, &n_inner, &max_leaf);
     if (st != BVR_OK) return st;
 
     // the ranges to copy
@@ -372,6 +376,7 @@ int bvr_upload_scene(BvrContext* ctx,
     ctx->n_nodes = n_nodes;
     ctx->tree_depth = depth;
     ctx->n_inner = n_inner;
+    ctx->max_leaf_models = max_leaf;
     ctx->has_scene = n_nodes > 0 && n_models > 0;
     ctx->scene_uploaded = true;
     return BVR_OK;
@@ -464,6 +469,7 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
     ctx->n_nodes = n_nodes;
     ctx->tree_depth = *ctx->depth_host;
     ctx->n_inner = n_models ? (uint32_t)(n_models - 1) : 0u;
+    ctx->max_leaf_models = n_models ? 1u : 0u;   // the GPU builder emits one sphere per leaf
     ctx->root_ref_host = (n_models == 1) ? (BVR_LEAF_BIT | 0u) : 0u;
     ctx->has_scene = n_models > 0;
     ctx->scene_uploaded = true;
@@ -586,10 +592,25 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
             BVR_CK(cudaMemsetAsync(ctx->pixel_counter.ptr, 0, sizeof(unsigned int), ctx->stream));
             // largest CTA whose stacks (and, when it fits, the scene) fit in shared memory
             const int forced = env_int("BVR_MK_THREADS", 0);
+            const int variant = env_int("BVR_MK_VARIANT", 3);
+            if (variant == 4) {
+                // two paths per lane; scenes it does not take (see megakernel_v4.cu) fall through to v3
+                const int cand4[3] = {768, 640, 512};
+                for (int ci = 0; ci < 3 && n < 0; ci++) {
+                    const int threads = forced ? forced : cand4[ci];
+                    n = launch_megakernel_v4(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth, ctx->max_leaf_models,
+                                             ctx->pixel_counter.as<unsigned int>(), threads,
+                                             (uint32_t)env_int("BVR_MK4_SHADE", 24), (uint32_t)env_int("BVR_MK4_STUCK", 6),
+                                             (uint32_t)env_int("BVR_MK4_SWITCH", 6), (uint32_t)env_int("BVR_MK_LEAF", 4),
+                                             ctx->sm_count, ctx->stream);
+                    if (forced) break;
+                }
+                if (n < 0) cudaGetLastError();
+            }
             const int candidates[4] = {1024, 768, 512, 256};
             for (int ci = 0; ci < 4 && n < 0; ci++) {
-                const int threads = forced ? forced : candidates[ci];
-                if (env_int("BVR_MK_VARIANT", 3) == 3)
+                const int threads = (forced && variant != 4) ? forced : candidates[ci];
+                if (variant != 2)
                     n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
                                              ctx->pixel_counter.as<unsigned int>(), threads,
                                              (uint32_t)env_int("BVR_MK_WAIT", 26), (uint32_t)env_int("BVR_MK_LEAF", 4),
@@ -598,7 +619,7 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
                     n = launch_megakernel_persistent(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
                                                      ctx->pixel_counter.as<unsigned int>(), threads,
                                                      (uint32_t)env_int("BVR_MK_WAIT", 28), ctx->sm_count, ctx->stream);
-                if (forced) break;
+                if (forced && variant != 4) break;
             }
             if (n < 0) cudaGetLastError();
         }

@@ -85,6 +85,11 @@ int launch_megakernel_persistent(const RenderParams& p, uint32_t n_inner, uint32
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
                          int sm_count, cudaStream_t stream);
+// two-paths-per-lane megakernel (v4); -1 when the scene does not qualify (see megakernel_v4.cu) -> use v3
+int launch_megakernel_v4(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
+                         uint32_t max_leaf_models, unsigned int* pixel_counter, int threads, uint32_t shade_lanes,
+                         uint32_t stuck_lanes, uint32_t switch_lanes, uint32_t leaf_batch_lanes, int sm_count,
+                         cudaStream_t stream);
 size_t wavefront_state_bytes(size_t slots);
 void wavefront_bind(WavefrontParams& w, void* state, size_t slots);
 // persistent per-CTA wavefront (cta_wavefront.cu): number of path slots it needs, and the launch
