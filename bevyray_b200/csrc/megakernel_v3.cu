@@ -57,13 +57,14 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
 // lo = tc - th, hi = tc + th — four FMA-pipe instructions instead of two FFMA + two FMNMX: the traversal loop is
 // bound by the ALU pipe (ncu r01_v3b: ALU 77 %, FMA 20 %), so the per-axis min/max is traded for arithmetic.
 // entry = max(lo.x, lo.y, lo.z, 0), exit = min(hi.x, hi.y, hi.z, closest); worth visiting iff entry <= exit.
-__device__ __forceinline__ bool box_cull(V3 inv, V3 noi, float closest_t, float cx, float cy, float cz, float hx,
+__device__ __forceinline__ bool box_cull(V3 inv, V3 ainv, V3 noi, float closest_t, float cx, float cy, float cz, float hx,
                                          float hy, float hz, float& entry) {
-    const float tcx = __fmaf_rn(cx, inv.x, noi.x), thx = hx * fabsf(inv.x);
-    const float tcy = __fmaf_rn(cy, inv.y, noi.y), thy = hy * fabsf(inv.y);
-    const float tcz = __fmaf_rn(cz, inv.z, noi.z), thz = hz * fabsf(inv.z);
-    entry = fmaxf(fmaxf(tcx - thx, tcy - thy), fmaxf(tcz - thz, 0.0f));
-    const float exit = fminf(fminf(tcx + thx, tcy + thy), fminf(tcz + thz, closest_t));
+    // three FFMA per axis: tc = c/d - o/d, lo = tc - h*|1/d|, hi = tc + h*|1/d|
+    const float tcx = __fmaf_rn(cx, inv.x, noi.x), tcy = __fmaf_rn(cy, inv.y, noi.y), tcz = __fmaf_rn(cz, inv.z, noi.z);
+    const float lox = __fmaf_rn(-hx, ainv.x, tcx), loy = __fmaf_rn(-hy, ainv.y, tcy), loz = __fmaf_rn(-hz, ainv.z, tcz);
+    const float hix = __fmaf_rn(hx, ainv.x, tcx), hiy = __fmaf_rn(hy, ainv.y, tcy), hiz = __fmaf_rn(hz, ainv.z, tcz);
+    entry = fmaxf(fmaxf(lox, loy), fmaxf(loz, 0.0f));
+    const float exit = fminf(fminf(hix, hiy), fminf(hiz, closest_t));
     return entry <= exit;
 }
 
@@ -108,21 +109,19 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     const uint32_t total_slots = tiles_x * tiles_y * 32u;
 
     int state = NEED_PIXEL;
-    uint32_t px = 0, ly = 0;
+    uint32_t pxy = 0;   // px | ly << 16
     float u = 0.0f, v = 0.0f;
     uint32_t rng = 0, sidx = 0, bounce = 0;
     V3 total = v3(0.0f, 0.0f, 0.0f);
     float total_depth = 0.0f, first_depth = BVR_INF;
-    uint32_t primary_id = 0xffffffffu;
-    float primary_t = BVR_INF;
     V3 throughput = v3(1.0f, 1.0f, 1.0f);
     Ray ray{v3(0, 0, 0), v3(0, 0, 1)};
-    V3 inv = v3(0, 0, 0), noi = v3(0, 0, 0);
+    V3 inv = v3(0, 0, 0), ainv = v3(0, 0, 0), noi = v3(0, 0, 0);
     float a = 1.0f;
     Hit closest{BVR_INF, 0xffffffffu};
     uint32_t cur = V3_NONE, pending = V3_NONE;
     uint32_t sp_addr = s_stack0;   // next free stack slot
-    unsigned long long rays = 0;
+    uint32_t rays = 0;
 
     for (;;) {
         // ======================= phase A: staged shading =======================
@@ -133,7 +132,11 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             if (state == SHADE) {
                 if (bounce == 0u) {
                     first_depth = closest.t;
-                    if (sidx == 0u) { primary_id = closest.t == BVR_INF ? 0xffffffffu : closest.model; primary_t = closest.t; }
+                    if (sidx == 0u && (p.out_primary_id || p.out_primary_depth)) {   // first sample's primary hit
+                        const size_t lpix = (size_t)(pxy >> 16) * cam.width + (pxy & 0xffffu);
+                        if (p.out_primary_id) p.out_primary_id[lpix] = closest.t == BVR_INF ? 0xffffffffu : closest.model;
+                        if (p.out_primary_depth) p.out_primary_depth[lpix] = closest.t;
+                    }
                 }
                 if (closest.t == BVR_INF) {
                     kind = K_MISS;
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         }
         // --- A4: pixel store (average, fused composite raytrace.wgsl:104-120) ---
         if (state == NEW_PATH && sidx >= cam.sample_count) {
+            const uint32_t px = pxy & 0xffffu, ly = pxy >> 16;
             const uint32_t gy = shard_global_row(p.shard, ly);
             const float n = (float)cam.sample_count;
             float4 out = make_float4(fdiv(total.x, n), fdiv(total.y, n), fdiv(total.z, n), 1.0f);
@@ -242,8 +246,10 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             const size_t lpix = (size_t)ly * cam.width + px;
             if (p.out_rgba) p.out_rgba[lpix] = out;
             if (p.out_rt_depth) p.out_rt_depth[lpix] = depth_avg;
-            if (p.out_primary_id) p.out_primary_id[lpix] = primary_id;
-            if (p.out_primary_depth) p.out_primary_depth[lpix] = primary_t;
+            if (cam.sample_count == 0u) {
+                if (p.out_primary_id) p.out_primary_id[lpix] = 0xffffffffu;
+                if (p.out_primary_depth) p.out_primary_depth[lpix] = BVR_INF;
+            }
             if (p.out_srgb8) p.out_srgb8[lpix] = store_srgb8(out);
             state = NEED_PIXEL;
         }
@@ -261,18 +267,17 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                     state = DONE;
                 } else {
                     const uint32_t tile = slot >> 5, within = slot & 31u;
-                    px = (tile % tiles_x) * 8u + (within & 7u);
-                    ly = (tile / tiles_x) * 4u + (within >> 3);
+                    const uint32_t px = (tile % tiles_x) * 8u + (within & 7u);
+                    const uint32_t ly = (tile / tiles_x) * 4u + (within >> 3);
                     const uint32_t gy = shard_global_row(p.shard, ly);
                     if (px < cam.width && ly < p.shard.rows && gy < cam.height) {
+                        pxy = px | (ly << 16);
                         u = pixel_u(cam, px);
                         v = pixel_v(cam, gy);
                         rng = pixel_seed(cam, u, v);
                         sidx = 0u;
                         total = v3(0.0f, 0.0f, 0.0f);
                         total_depth = 0.0f;
-                        primary_id = 0xffffffffu;
-                        primary_t = BVR_INF;
                         state = NEW_PATH;
                     }
                 }
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             // 1/d feeds the box tests only (culling), so the approximate reciprocal (MUFU.RCP, 1 ulp) is
             // enough: boxes are padded by 0.1, rounding is ~1e-7 relative
             inv = v3(rcp_approx(ray.d.x), rcp_approx(ray.d.y), rcp_approx(ray.d.z));
+            ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
             noi = v3(-(ray.o.x * inv.x), -(ray.o.y * inv.y), -(ray.o.z * inv.z));
             a = vdot(ray.d, ray.d);
             closest.t = BVR_INF;
@@ -325,8 +331,8 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                             r0 = __float_as_uint(q3.x); r1 = __float_as_uint(q3.y);
                         }
                         float d0, d1;
-                        const bool h0 = box_cull(inv, noi, closest.t, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, d0);
-                        const bool h1 = box_cull(inv, noi, closest.t, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, d1);
+                        const bool h0 = box_cull(inv, ainv, noi, closest.t, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, d0);
+                        const bool h1 = box_cull(inv, ainv, noi, closest.t, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, d1);
                         const bool first0 = d0 < d1;         // ties go to the second child (reference LIFO order)
                         if (h0 && h1) {
                             sts64(sp_addr, first0 ? r1 : r0, __float_as_uint(first0 ? d1 : d0));
@@ -375,7 +381,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         }
     }
 
-    unsigned long long sum = rays;
+    unsigned long long sum = rays;   // < 2^32 rays per lane
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
     if (lane == 0u && p.ray_counter && sum) atomicAdd(p.ray_counter, sum);
@@ -410,6 +416,7 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
                          int sm_count, cudaStream_t stream) {
+    if (p.cam.width > 0xffffu || p.shard.rows > 0xffffu) return -1;   // pixel packed as px | ly << 16
     Tuning t{shade_wait_lanes, leaf_batch_lanes};
     switch (threads) {
         case 256: return launch_v3<256>(p, n_inner, n_models, tree_depth, pixel_counter, t, sm_count, stream);
