@@ -59,6 +59,10 @@ struct BvrContext {
     // scene, reference layout (raw bytes in HBM) and the derived traversal layout
     DeviceBuffer raw_models, raw_materials, raw_nodes;
     DeviceBuffer spheres, sphere_material, pairs, pairs_ch, inner_id, block_sums, root_ref;
+    DeviceBuffer pairs_q, nodes4_q, qgrid;              // 32-byte quantised records + their grid (big scenes), flag at qgrid[8]
+    unsigned int* q16_bad_host = nullptr;     // pinned copy of the 'does not qualify' flag
+    bool q16_built = false, q16_pending = false;
+    cudaEvent_t q16_done = nullptr;
     size_t n_models = 0, n_materials = 0, n_nodes = 0;
     bool scene_uploaded = false;
     bool has_scene = false;
@@ -186,6 +190,29 @@ int h2d(BvrContext* ctx, void* dst, const void* src, size_t bytes, PinnedBuffer&
     return BVR_OK;
 }
 
+// Scenes too large for shared memory also get 32-byte quantised records (one 256-bit load per node visit,
+// megakernel_v3.cu MODE 2).  Returns the number of kernels launched; the verdict arrives through q16_done.
+int derive_q16(BvrContext* ctx, size_t n_models, size_t n_nodes, uint32_t n_inner, uint32_t max_leaf, int* launches) {
+    ctx->q16_built = false;
+    ctx->q16_pending = false;
+    const size_t scene_bytes = (size_t)n_inner * 64u + n_models * 20u;
+    if (env_int("BVR_NO_Q16", 0) || scene_bytes <= 160u * 1024u || n_inner > (1u << 20) || n_models > (1u << 20) || max_leaf > 1u)
+        return BVR_OK;
+    BVR_CK(ctx->pairs_q.ensure((size_t)n_inner * 32u + 32u));
+    BVR_CK(ctx->qgrid.ensure(16 * sizeof(float)));
+    uint32_t* bad = ctx->qgrid.as<uint32_t>() + 8;
+    *launches += launch_derive_pairs_q16(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+                                         ctx->pairs_q.as<uint4>(), ctx->qgrid.as<float>(), bad, ctx->stream);
+    BVR_CK(ctx->nodes4_q.ensure((size_t)n_inner * 64u + 64u));
+    *launches += launch_derive_nodes4_q16(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+                                          ctx->pairs_q.as<uint4>(), ctx->nodes4_q.as<uint4>(), ctx->stream);
+    BVR_CK(cudaMemcpyAsync(ctx->q16_bad_host, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BVR_CK(cudaEventRecord(ctx->q16_done, ctx->stream));
+    ctx->q16_built = true;
+    ctx->q16_pending = true;
+    return BVR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -229,6 +256,8 @@ int bvr_create(int device, BvrContext** out_ctx) {
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->ray_counter_host, sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->wf_host_counts, 8 * sizeof(unsigned int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->depth_host, sizeof(unsigned int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->q16_bad_host, sizeof(unsigned int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->q16_done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaGetLastError();
         bvr_destroy(ctx);
@@ -247,12 +276,14 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->pairs_ch, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
     if (ctx->ray_counter_host) cudaFreeHost(ctx->ray_counter_host);
     if (ctx->wf_host_counts) cudaFreeHost(ctx->wf_host_counts);
+    if (ctx->q16_bad_host) cudaFreeHost(ctx->q16_bad_host);
+    if (ctx->q16_done) cudaEventDestroy(ctx->q16_done);
     if (ctx->depth_host) cudaFreeHost(ctx->depth_host);
     cudaEvent_t evs[] = {ctx->ev_render0, ctx->ev_render1, ctx->ev_upload0, ctx->ev_upload1, ctx->upload_done};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
@@ -367,6 +398,10 @@ int bvr_upload_scene(BvrContext* ctx,
                                      : 0u;   // node 0 is the first inner node -> dense id 0
         }
     }
+    if (nodes_dirty || !partial) {
+        st = derive_q16(ctx, n_models, n_nodes, n_inner, max_leaf, &launches);
+        if (st != BVR_OK) return st;
+    }
     BVR_CK(cudaGetLastError());
     BVR_CK(cudaEventRecord(ctx->ev_upload1, ctx->stream));
     ctx->upload_timed = true;
@@ -453,6 +488,10 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
         launches += launch_derive_pairs(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
                                         ctx->block_sums.as<uint32_t>(), ctx->pairs.as<float4>(), ctx->pairs_ch.as<float4>(),
                                         ctx->root_ref.as<uint32_t>(), ctx->stream);
+        {
+            int st = derive_q16(ctx, n_models, n_nodes, (uint32_t)(n_models - 1), 1u, &launches);
+            if (st != BVR_OK) return st;
+        }
         BVR_CK(cudaMemcpyAsync(ctx->depth_host, d_depth, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         if (out_nodes) {
             BVR_CK(cudaMemcpyAsync(out_nodes, ctx->raw_nodes.ptr, n_nodes * sizeof(BvrBvhNode), cudaMemcpyDeviceToHost, ctx->stream));
@@ -497,6 +536,14 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     p.scene.spheres = ctx->spheres.as<float4>();
     p.scene.sphere_material = ctx->sphere_material.as<uint32_t>();
     p.scene.materials = ctx->raw_materials.as<float4>();
+    if (ctx->q16_built) {
+        if (ctx->q16_pending) { BVR_CK(cudaEventSynchronize(ctx->q16_done)); ctx->q16_pending = false; }
+        if (*ctx->q16_bad_host == 0u) {
+            p.scene.pairs_q = ctx->pairs_q.as<uint4>();
+            p.scene.nodes4_q = env_int("BVR_NO_BVH4", 0) ? nullptr : ctx->nodes4_q.as<uint4>();
+            p.scene.qgrid = ctx->qgrid.as<float>();
+        }
+    }
     p.scene.root_ref = ctx->root_ref_host;
     p.scene.n_materials = (uint32_t)ctx->n_materials;
     p.scene.has_scene = ctx->has_scene ? 1u : 0u;

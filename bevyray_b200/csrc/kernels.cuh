@@ -70,6 +70,15 @@ int launch_derive_spheres(const RawModel* models, uint32_t n, float4* spheres, u
 int launch_derive_pairs(const RawNode* nodes, uint32_t n_nodes, uint32_t* inner_id, uint32_t* block_sums,
                         float4* pairs, float4* pairs_ch, uint32_t* root_ref_out, cudaStream_t stream);
 
+// 32-byte quantised records for scenes that are walked in HBM/L2 (after launch_derive_pairs: needs inner_id);
+// grid = 8 floats (base.xyz, -, step.xyz, -); *bad != 0 afterwards -> the scene does not qualify
+int launch_derive_pairs_q16(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, uint4* pairs_q,
+                            float* grid, uint32_t* bad, cudaStream_t stream);
+
+// 64-byte 4-wide records (the children's children) from the 32-byte ones
+int launch_derive_nodes4_q16(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, const uint4* pairs_q,
+                             uint4* nodes4, cudaStream_t stream);
+
 // ---- GPU BVH builder (bvh_build.cu) ----
 size_t bvh_build_scratch_bytes(uint32_t n_models);
 int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, void* scratch, uint32_t** depth_out,

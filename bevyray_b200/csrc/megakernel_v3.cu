@@ -49,6 +49,25 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+// 256-bit read-only global load (sm_100: LDG.E.256): one request per 32-byte sector instead of two 16-byte ones
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg256u(const uint4* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t a) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
@@ -68,15 +87,47 @@ __device__ __forceinline__ bool box_cull(V3 inv, V3 ainv, V3 noi, float closest_
     return entry <= exit;
 }
 
+// Slab test on a 32-byte quantised record (scene_kernels.cu: build_pairs_q16_kernel).  A coordinate word holds
+// lo | hi << 16 on the scene's 16-bit grid; PRMT builds the float 2^23 + q from the half the ray enters (selN)
+// or leaves (selF) through, and ONE FFMA maps it to the ray parameter: t = (2^23 + q) * (step/d) + C with
+// C = (base - o)/d - 2^23 * step/d.  C carries up to half a grid step of rounding error, which the extra step
+// of outward rounding in the records absorbs.  No per-axis min/max: the ray's octant picks near and far.
+__device__ __forceinline__ bool box_cull_q16(uint32_t wx, uint32_t wy, uint32_t wz, V3 sinv, V3 cq, uint32_t snx,
+                                             uint32_t sny, uint32_t snz, uint32_t sfx, uint32_t sfy, uint32_t sfz,
+                                             float closest_t, float& entry) {
+    const uint32_t magic = 0x00004b00u;
+    const float tnx = __fmaf_rn(__uint_as_float(__byte_perm(wx, magic, snx)), sinv.x, cq.x);
+    const float tny = __fmaf_rn(__uint_as_float(__byte_perm(wy, magic, sny)), sinv.y, cq.y);
+    const float tnz = __fmaf_rn(__uint_as_float(__byte_perm(wz, magic, snz)), sinv.z, cq.z);
+    const float tfx = __fmaf_rn(__uint_as_float(__byte_perm(wx, magic, sfx)), sinv.x, cq.x);
+    const float tfy = __fmaf_rn(__uint_as_float(__byte_perm(wy, magic, sfy)), sinv.y, cq.y);
+    const float tfz = __fmaf_rn(__uint_as_float(__byte_perm(wz, magic, sfz)), sinv.z, cq.z);
+    entry = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    const float exit = fminf(fminf(tfx, tfy), fminf(tfz, closest_t));
+    return entry <= exit;
+}
+
+#define Q16_LEAF 0x100000u
+#define Q16_NONE 0x200000u
+#define Q16_REF_MASK 0x1fffffu
+
 struct Tuning {
     uint32_t shade_wait_lanes;   // leave phase B when this many lanes wait for shading
     uint32_t leaf_batch_lanes;   // test parked leaves when this many lanes hold one
 };
 
-template <int THREADS, bool SMEM_SCENE>
+// MODE 0: scene in shared memory (64-byte fp32 records).  MODE 1: scene in HBM/L2, 64-byte fp32 records, 8-byte
+// stack entries.  MODE 2: scene in HBM/L2, 32-byte quantised records (one 256-bit load per visit), 4-byte stack
+// entries (11 bits of distance | 21 bits of child ref).  MODE 3: as 2, on the 64-byte 4-wide records (two 256-bit
+// loads issued together): two levels of the tree per dependent fetch, the children sorted as packed 32-bit keys.
+template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, unsigned int* __restrict__ pixel_counter,
                                                          const uint32_t n_inner, const uint32_t n_models,
                                                          const Tuning tune) {
+    constexpr bool SMEM_SCENE = MODE == 0;
+    constexpr bool Q16 = MODE >= 2;
+    constexpr bool W4 = MODE == 3;
+    constexpr uint32_t NONE = Q16 ? Q16_NONE : V3_NONE;
     extern __shared__ float4 smem[];
     const CameraParams& cam = p.cam;
     const unsigned full = 0xffffffffu;
@@ -101,8 +152,15 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         __syncthreads();
     }
     // per-lane stack: entry k of lane t at s_stack0 + k * STACK_STRIDE (interleaved: conflict-free)
-    constexpr uint32_t STACK_STRIDE = THREADS * 8u;
-    const uint32_t s_stack0 = smem_addr(sm_cursor) + tid * 8u;
+    constexpr uint32_t STACK_STRIDE = THREADS * (Q16 ? 4u : 8u);
+    const uint32_t s_stack0 = smem_addr(sm_cursor) + tid * (Q16 ? 4u : 8u);
+    // MODE 2: the quantisation grid and the root in 21-bit form
+    const float qbx = Q16 ? sv.qgrid[0] : 0.f, qby = Q16 ? sv.qgrid[1] : 0.f, qbz = Q16 ? sv.qgrid[2] : 0.f;
+    const float qsx = Q16 ? sv.qgrid[4] : 0.f, qsy = Q16 ? sv.qgrid[5] : 0.f, qsz = Q16 ? sv.qgrid[6] : 0.f;
+    const uint32_t root = !sv.has_scene ? NONE
+                          : (Q16 ? ((sv.root_ref & BVR_LEAF_BIT) ? (Q16_LEAF | (sv.root_ref & 0xfffffu)) : sv.root_ref)
+                                 : sv.root_ref);
+    uint32_t snx = 0, sny = 0, snz = 0, sfx = 0, sfy = 0, sfz = 0;   // MODE 2: PRMT selectors of the near / far halves
     const uint32_t s_pairs = SMEM_SCENE ? smem_addr(sv.pairs_ch) : 0u;
 
     const uint32_t tiles_x = (cam.width + 7u) / 8u, tiles_y = (p.shard.rows + 3u) / 4u;
@@ -119,7 +177,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     V3 inv = v3(0, 0, 0), ainv = v3(0, 0, 0), noi = v3(0, 0, 0);
     float a = 1.0f;
     Hit closest{BVR_INF, 0xffffffffu};
-    uint32_t cur = V3_NONE, pending = V3_NONE;
+    uint32_t cur = NONE, pending = NONE;
     uint32_t sp_addr = s_stack0;   // next free stack slot
     uint32_t rays = 0;
 
@@ -297,14 +355,24 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             // 1/d feeds the box tests only (culling), so the approximate reciprocal (MUFU.RCP, 1 ulp) is
             // enough: boxes are padded by 0.1, rounding is ~1e-7 relative
             inv = v3(rcp_approx(ray.d.x), rcp_approx(ray.d.y), rcp_approx(ray.d.z));
-            ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
-            noi = v3(-(ray.o.x * inv.x), -(ray.o.y * inv.y), -(ray.o.z * inv.z));
+            if (Q16) {
+                // inv := step/d, noi := (base - o)/d - 2^23 * step/d (see box_cull_q16); selectors by octant
+                snx = inv.x >= 0.0f ? 0x5410u : 0x5432u; sfx = snx ^ 0x0022u;
+                sny = inv.y >= 0.0f ? 0x5410u : 0x5432u; sfy = sny ^ 0x0022u;
+                snz = inv.z >= 0.0f ? 0x5410u : 0x5432u; sfz = snz ^ 0x0022u;
+                const V3 bo = v3((qbx - ray.o.x) * inv.x, (qby - ray.o.y) * inv.y, (qbz - ray.o.z) * inv.z);
+                inv = v3(qsx * inv.x, qsy * inv.y, qsz * inv.z);
+                noi = v3(__fmaf_rn(-8388608.0f, inv.x, bo.x), __fmaf_rn(-8388608.0f, inv.y, bo.y), __fmaf_rn(-8388608.0f, inv.z, bo.z));
+            } else {
+                ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
+                noi = v3(-(ray.o.x * inv.x), -(ray.o.y * inv.y), -(ray.o.z * inv.z));
+            }
             a = vdot(ray.d, ray.d);
             closest.t = BVR_INF;
             closest.model = 0xffffffffu;
             sp_addr = s_stack0;
-            pending = V3_NONE;
-            cur = sv.has_scene ? sv.root_ref : V3_NONE;
+            pending = NONE;
+            cur = root;
             rays++;
             state = TRAVERSE;
         }
@@ -316,47 +384,95 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             for (int rep = 0; rep < BVR_STEPS_PER_VOTE; rep++) {
                 if (state == TRAVERSE) {
                     uint32_t c = cur;
-                    if (c < V3_NONE) {                       // inner node: test both children
-                        float4 q0, q1, q2;
+                    if (Q16 ? c < Q16_LEAF : c < V3_NONE) {  // inner node: test both children
                         uint32_t r0, r1;
-                        if (SMEM_SCENE) {
-                            const uint32_t na = s_pairs + c * 64u;
-                            q0 = lds128(na); q1 = lds128(na + 16u); q2 = lds128(na + 32u);
-                            const uint2 rr = lds64(na + 48u);
-                            r0 = rr.x; r1 = rr.y;
-                        } else {
-                            const float4* nd = sv.pairs_ch + 4u * c;
-                            q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2);
-                            const float4 q3 = __ldg(nd + 3);
-                            r0 = __float_as_uint(q3.x); r1 = __float_as_uint(q3.y);
-                        }
                         float d0, d1;
-                        const bool h0 = box_cull(inv, ainv, noi, closest.t, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, d0);
-                        const bool h1 = box_cull(inv, ainv, noi, closest.t, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, d1);
+                        bool h0, h1;
+                        if (W4) {
+                            // four children: key = 11 bits of entry distance | 21 bits of ref, 0xffffffff = not entered
+                            uint4 qa, qb, qc, qd;
+                            const uint4* np = sv.nodes4_q + 4u * c;
+                            ldg256u(np, qa, qb);
+                            ldg256u(np + 2, qc, qd);
+                            float e;
+                            uint32_t k0 = box_cull_q16(qa.x, qa.y, qa.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
+                                              ? (((__float_as_uint(e) >> 20) << 21) | qa.w) : 0xffffffffu;
+                            uint32_t k1 = box_cull_q16(qb.x, qb.y, qb.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
+                                              ? (((__float_as_uint(e) >> 20) << 21) | qb.w) : 0xffffffffu;
+                            uint32_t k2 = box_cull_q16(qc.x, qc.y, qc.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
+                                              ? (((__float_as_uint(e) >> 20) << 21) | qc.w) : 0xffffffffu;
+                            uint32_t k3 = box_cull_q16(qd.x, qd.y, qd.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
+                                              ? (((__float_as_uint(e) >> 20) << 21) | qd.w) : 0xffffffffu;
+                            // sorting network, ascending
+                            uint32_t t0;
+                            t0 = min(k0, k1); k1 = max(k0, k1); k0 = t0;
+                            t0 = min(k2, k3); k3 = max(k2, k3); k2 = t0;
+                            t0 = min(k0, k2); k2 = max(k0, k2); k0 = t0;
+                            t0 = min(k1, k3); k3 = max(k1, k3); k1 = t0;
+                            t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
+                            if (k3 != 0xffffffffu) { sts32(sp_addr, k3); sp_addr += STACK_STRIDE; }
+                            if (k2 != 0xffffffffu) { sts32(sp_addr, k2); sp_addr += STACK_STRIDE; }
+                            if (k1 != 0xffffffffu) { sts32(sp_addr, k1); sp_addr += STACK_STRIDE; }
+                            c = k0 != 0xffffffffu ? (k0 & Q16_REF_MASK) : NONE;
+                            r0 = r1 = 0u; d0 = d1 = 0.0f; h0 = h1 = false;
+                        } else if (Q16) {
+                            uint4 qa, qb;
+                            ldg256u(sv.pairs_q + 2u * c, qa, qb);
+                            r0 = qa.w; r1 = qb.w;
+                            h0 = box_cull_q16(qa.x, qa.y, qa.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, d0);
+                            h1 = box_cull_q16(qb.x, qb.y, qb.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, d1);
+                        } else {
+                            float4 q0, q1, q2;
+                            if (SMEM_SCENE) {
+                                const uint32_t na = s_pairs + c * 64u;
+                                q0 = lds128(na); q1 = lds128(na + 16u); q2 = lds128(na + 32u);
+                                const uint2 rr = lds64(na + 48u);
+                                r0 = rr.x; r1 = rr.y;
+                            } else {
+                                const float4* nd = sv.pairs_ch + 4u * c;
+                                float4 q3;
+                                ldg256(nd, q0, q1);
+                                ldg256(nd + 2, q2, q3);
+                                r0 = __float_as_uint(q3.x); r1 = __float_as_uint(q3.y);
+                            }
+                            h0 = box_cull(inv, ainv, noi, closest.t, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, d0);
+                            h1 = box_cull(inv, ainv, noi, closest.t, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, d1);
+                        }
                         const bool first0 = d0 < d1;         // ties go to the second child (reference LIFO order)
-                        if (h0 && h1) {
-                            sts64(sp_addr, first0 ? r1 : r0, __float_as_uint(first0 ? d1 : d0));
+                        if (W4) {
+                        } else if (h0 && h1) {
+                            if (Q16) {
+                                // far child: 11 bits of distance, rounded towards zero (conservative at pop time)
+                                sts32(sp_addr, ((__float_as_uint(first0 ? d1 : d0) >> 20) << 21) | (first0 ? r1 : r0));
+                            } else {
+                                sts64(sp_addr, first0 ? r1 : r0, __float_as_uint(first0 ? d1 : d0));
+                            }
                             sp_addr += STACK_STRIDE;
                             c = first0 ? r0 : r1;
                         } else {
-                            c = h0 ? r0 : (h1 ? r1 : V3_NONE);
+                            c = h0 ? r0 : (h1 ? r1 : NONE);
                         }
                     }
-                    if ((int)c < 0) {                        // leaf: park it, or wait for the batch test
-                        if (pending == V3_NONE) { pending = c; c = V3_NONE; }
+                    if (Q16 ? (c & Q16_LEAF) != 0u : (int)c < 0) {   // leaf: park it, or wait for the batch test
+                        if (pending == NONE) { pending = c; c = NONE; }
                         else blocked = true;
                     }
-                    if (c == V3_NONE) {
+                    if (c == NONE) {
                         // pop until an entry survives the cull: a culled entry costs ~6 instructions here
                         // instead of a whole step (ncu r01_v3b: 18.5 steps per ray, half of them dead pops)
                         while (sp_addr != s_stack0) {
                             sp_addr -= STACK_STRIDE;
-                            const uint2 e = lds64(sp_addr);
-                            if (__uint_as_float(e.y) < closest.t) { c = e.x; break; }
+                            if (Q16) {
+                                const uint32_t e = lds32(sp_addr);
+                                if (__uint_as_float((e >> 21) << 20) < closest.t) { c = e & Q16_REF_MASK; break; }
+                            } else {
+                                const uint2 e = lds64(sp_addr);
+                                if (__uint_as_float(e.y) < closest.t) { c = e.x; break; }
+                            }
                         }
-                        if (c == V3_NONE) {
-                            if (pending == V3_NONE) state = SHADE;   // traversal finished
-                            else blocked = true;                     // only the parked leaf is left
+                        if (c == NONE) {
+                            if (pending == NONE) state = SHADE;   // traversal finished
+                            else blocked = true;                  // only the parked leaf is left
                         }
                     }
                     cur = c;
@@ -368,9 +484,9 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             if (trav == 0u) break;
             const uint32_t nblk = (uint32_t)__popc(blk), ntrav = (uint32_t)__popc(trav);
             if (nblk >= tune.leaf_batch_lanes || nblk == ntrav) {
-                if (state == TRAVERSE && pending != V3_NONE) {
-                    test_leaf(sv, ray, a, pending, closest);
-                    pending = V3_NONE;
+                if (state == TRAVERSE && pending != NONE) {
+                    test_leaf(sv, ray, a, Q16 ? (pending & 0xfffffu) : pending, closest);
+                    pending = NONE;
                 }
             }
             if (32u - ntrav >= tune.shade_wait_lanes) {
@@ -390,14 +506,18 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
 template <int THREADS>
 int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
               unsigned int* pixel_counter, Tuning tune, int sm_count, cudaStream_t stream) {
-    const uint32_t stack_cap = tree_depth + 1u;
+    uint32_t stack_cap = tree_depth + 1u;
     const size_t scene_bytes = (size_t)(4u * n_inner + n_models + 2u * p.scene.n_materials + (n_models + 3u) / 4u) * 16u;
-    const size_t stack_bytes = (size_t)THREADS * stack_cap * sizeof(uint2);
     const size_t max_smem = 227u * 1024u;
-    const bool smem_scene = scene_bytes + stack_bytes <= max_smem;
+    const bool smem_scene = scene_bytes + (size_t)THREADS * stack_cap * sizeof(uint2) <= max_smem;
+    const bool q16 = !smem_scene && p.scene.pairs_q != nullptr;   // quantised records qualify (bvr_api.cu)
+    const bool w4 = q16 && p.scene.nodes4_q != nullptr;
+    if (w4) stack_cap = 3u * ((tree_depth + 1u) / 2u) + 2u;       // up to three siblings parked per 4-wide level
+    const size_t stack_bytes = (size_t)THREADS * stack_cap * (q16 ? sizeof(uint32_t) : sizeof(uint2));
     const size_t smem = (smem_scene ? scene_bytes : 0) + stack_bytes;
     if (smem > max_smem) return -1;
-    auto kern = smem_scene ? megakernel_v3<THREADS, true> : megakernel_v3<THREADS, false>;
+    auto kern = smem_scene ? megakernel_v3<THREADS, 0>
+                           : (w4 ? megakernel_v3<THREADS, 3> : (q16 ? megakernel_v3<THREADS, 2> : megakernel_v3<THREADS, 1>));
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     int blocks_per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem) != cudaSuccess || blocks_per_sm < 1)

@@ -127,7 +127,108 @@ __global__ void build_pairs_kernel(const RawNode* __restrict__ nodes, uint32_t n
     och[3] = out[3];
 }
 
+// Quantisation grid of the 32-byte records: 65536 steps per axis across the root box plus two steps of margin on
+// either side (so that the outward rounding below never has to clamp inside the root box).
+struct QGrid { float base[3], step[3]; };
+
+__device__ __forceinline__ QGrid make_qgrid(const RawNode& root) {
+    QGrid g;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        g.step[k] = fmaxf(__fdiv_ru(__fsub_ru(root.mx[k], root.mn[k]), 65531.0f), 1e-30f);
+        g.base[k] = __fsub_rd(root.mn[k], __fmul_ru(2.0f, g.step[k]));
+    }
+    return g;
+}
+
+// pass 4b: one 32-byte record per inner node: child boxes as 16-bit grid coordinates, rounded OUTWARDS by one
+// extra step (the decode in the kernel is one FFMA whose constant term carries up to half a step of rounding
+// error, megakernel_v3.cu).  Word layout: (c0.x, c0.y, c0.z, ref0, c1.x, c1.y, c1.z, ref1), each coordinate word
+// = lo | hi << 16; refs in 21-bit form: bit 20 = leaf, bits 0-19 = inner record / first (only) model.
+// `bad` is raised when a box leaves the root box or a ref does not fit: the fp32 records are used then.
+__global__ void build_pairs_q16_kernel(const RawNode* __restrict__ nodes, uint32_t n,
+                                       const uint32_t* __restrict__ inner_id, uint4* __restrict__ pairs_q,
+                                       float* __restrict__ grid_out, uint32_t* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const QGrid g = make_qgrid(nodes[0]);
+    if (i == 0u) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { grid_out[k] = g.base[k]; grid_out[4 + k] = g.step[k]; }
+        grid_out[3] = 0.0f; grid_out[7] = 0.0f;
+    }
+    const RawNode nd = nodes[i];
+    if (nd.model_count != 0u) {
+        if (nd.model_count > 1u || nd.index >= (1u << 20)) *bad = 1u;
+        return;
+    }
+    uint32_t w[8];
+    bool is_bad = inner_id[i] >= (1u << 20);
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const RawNode ch = nodes[nd.index + (uint32_t)c];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            // floor / ceil of the exact grid coordinate, then one step outwards
+            const float lo = floorf(__fdiv_rd(__fsub_rd(ch.mn[k], g.base[k]), g.step[k])) - 1.0f;
+            const float hi = ceilf(__fdiv_ru(__fsub_ru(ch.mx[k], g.base[k]), g.step[k])) + 1.0f;
+            if (!(lo >= 0.0f) || !(hi <= 65535.0f) || !(lo <= hi)) is_bad = true;   // outside the grid, or NaN
+            const uint32_t ql = (uint32_t)fminf(fmaxf(lo, 0.0f), 65535.0f), qh = (uint32_t)fminf(fmaxf(hi, 0.0f), 65535.0f);
+            w[c * 4 + k] = ql | (qh << 16);
+        }
+        const uint32_t cid = inner_id[nd.index + (uint32_t)c];
+        w[c * 4 + 3] = ch.model_count > 0u ? ((1u << 20) | (ch.index & 0xfffffu)) : cid;
+    }
+    if (is_bad) *bad = 1u;
+    uint4* out = pairs_q + 2u * inner_id[i];
+    out[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    out[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// pass 4c: 4-wide records for the latency-bound walk of big scenes.  The record of inner node N holds the
+// children of N's two children (a leaf child stays as it is, next to an empty slot), i.e. two 32-byte pair
+// records side by side: the walk descends two levels of the reference tree per dependent 64-byte fetch.  Only
+// the records of even-depth nodes are ever reached from the root; the others are built and never read.
+__global__ void build_nodes4_q16_kernel(const RawNode* __restrict__ nodes, uint32_t n,
+                                        const uint32_t* __restrict__ inner_id, const uint4* __restrict__ pairs_q,
+                                        uint4* __restrict__ nodes4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RawNode nd = nodes[i];
+    if (nd.model_count != 0u) return;
+    const uint32_t id = inner_id[i];
+    uint4* out = nodes4 + 4u * id;
+    const uint4 empty = make_uint4(0x0000ffffu, 0x0000ffffu, 0x0000ffffu, 0x200000u);   // lo > hi: never entered
+#pragma unroll
+    for (uint32_t s = 0; s < 2u; s++) {
+        const uint32_t x = nd.index + s;
+        if (nodes[x].model_count > 0u) {
+            out[2u * s] = pairs_q[2u * id + s];
+            out[2u * s + 1u] = empty;
+        } else {
+            const uint32_t xid = inner_id[x];
+            out[2u * s] = pairs_q[2u * xid];
+            out[2u * s + 1u] = pairs_q[2u * xid + 1u];
+        }
+    }
+}
+
 }  // namespace
+
+int launch_derive_nodes4_q16(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, const uint4* pairs_q,
+                             uint4* nodes4, cudaStream_t stream) {
+    if (n_nodes == 0) return 0;
+    build_nodes4_q16_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(nodes, n_nodes, inner_id, pairs_q, nodes4);
+    return 1;
+}
+
+int launch_derive_pairs_q16(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, uint4* pairs_q,
+                            float* grid, uint32_t* bad, cudaStream_t stream) {
+    if (n_nodes == 0) return 0;
+    cudaMemsetAsync(bad, 0, sizeof(uint32_t), stream);
+    build_pairs_q16_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(nodes, n_nodes, inner_id, pairs_q, grid, bad);
+    return 1;
+}
 
 int launch_derive_spheres(const RawModel* models, uint32_t n, float4* spheres, uint32_t* sphere_material,
                           cudaStream_t stream) {

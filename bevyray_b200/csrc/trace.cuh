@@ -30,6 +30,9 @@ struct SceneView {
     const float4* __restrict__ pairs;            // 4 x float4 per inner node: child boxes as (min, max)
     const float4* __restrict__ pairs_ch;         // same records with the boxes as (centre, half extent):
                                                  //   q0 = (c0.xyz, h0.x) q1 = (h0.yz, c1.xy) q2 = (c1.z, h1.xyz) q3 = refs
+    const uint4* __restrict__ pairs_q;           // 32-byte records on a 16-bit grid (scene_kernels.cu), or null
+    const uint4* __restrict__ nodes4_q;          // 64-byte 4-wide records on the same grid, or null
+    const float* __restrict__ qgrid;             // (base.xyz, -, step.xyz, -) of that grid
     const float4* __restrict__ spheres;          // (centre.xyz, radius) per model
     const uint32_t* __restrict__ sphere_material;  // Model::material_id per model
     const float4* __restrict__ materials;        // 2 x float4 per material (reference bytes)

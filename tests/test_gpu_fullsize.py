@@ -79,3 +79,32 @@ def test_c3_size_4k_band(bvr, oracle, ctx, rtiow):
     want, _ = oracle.render(rtiow.models, rtiow.materials, rtiow.nodes, cam, bvr.make_level(3), win, W, rows=(gy, gy + 4))
     assert np.array_equal(bits(part["rgba"][ly:ly + 4]), bits(want["rgba"][gy:gy + 4]))
     assert np.array_equal(part["primary_id"][ly:ly + 4], want["primary_id"][gy:gy + 4])
+
+
+def test_c4_size_full_frame_against_oracle(bvr, oracle, ctx):
+    """BASELINE configs[3] scene and resolution (2^20 random spheres, 1920x1080, 10 bounces) at 1 spp: the whole
+    frame against the oracle, for the production path of scenes walked in HBM/L2 (4-wide 16-bit records, 4-byte
+    stack entries), the 2-wide quantised records, the fp32 records and the reference-order kernel."""
+    import os
+    W, H = 1920, 1080
+    scene = bvr.Scene.random(7, 1 << 20, 200.0, 0.05, 0.25)
+    cam = bvr.make_camera(position=(0.0, 0.0, 130.0), target=(0.0, 0.0, 0.0), aspect=W / H, sample_count=1, bounces=10)
+    win = bvr.make_window(0.37, H)
+    want, cnt = oracle.render(scene.models, scene.materials, scene.nodes, cam, bvr.make_level(3), win, W)
+    assert cnt["stack_truncations"] == 0
+    ctx.upload_scene(scene.models, scene.materials, scene.nodes)
+    variants = [({}, 0), ({"BVR_NO_BVH4": "1"}, 0), ({"BVR_NO_Q16": "1"}, 0), ({}, 1)]
+    try:
+        for env, traversal in variants:
+            for k in ("BVR_NO_BVH4", "BVR_NO_Q16"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            if "BVR_NO_Q16" in env:
+                ctx.upload_scene(scene.models, scene.materials, scene.nodes)   # the records are chosen at upload
+            got = ctx.render(cam, 3, win, bvr.make_options(W, traversal=traversal))
+            for k in ("primary_id", "primary_depth", "rt_depth", "rgba"):
+                assert np.array_equal(bits(got[k]), bits(want[k])), (env, traversal, k)
+            assert ctx.stats()["rays"] == cnt["rays"]
+    finally:
+        for k in ("BVR_NO_BVH4", "BVR_NO_Q16"):
+            os.environ.pop(k, None)
