@@ -59,6 +59,8 @@ struct BvrContext {
     // scene, reference layout (raw bytes in HBM) and the derived traversal layout
     DeviceBuffer raw_models, raw_materials, raw_nodes;
     DeviceBuffer spheres, sphere_material, pairs, pairs_ch, inner_id, block_sums, root_ref;
+    DeviceBuffer nodes4_ch;                   // 4-wide fp32 records (scenes staged in shared memory)
+    bool nodes4_ch_built = false;
     DeviceBuffer pairs_q, nodes4_q, qgrid;              // 32-byte quantised records + their grid (big scenes), flag at qgrid[8]
     unsigned int* q16_bad_host = nullptr;     // pinned copy of the 'does not qualify' flag
     bool q16_built = false, q16_pending = false;
@@ -195,6 +197,13 @@ int h2d(BvrContext* ctx, void* dst, const void* src, size_t bytes, PinnedBuffer&
 int derive_q16(BvrContext* ctx, size_t n_models, size_t n_nodes, uint32_t n_inner, uint32_t max_leaf, int* launches) {
     ctx->q16_built = false;
     ctx->q16_pending = false;
+    ctx->nodes4_ch_built = false;
+    if (n_inner >= 1u && n_inner <= 1024u && n_models <= 1024u && max_leaf <= 1u) {
+        BVR_CK(ctx->nodes4_ch.ensure((size_t)n_inner * 112u));
+        *launches += launch_derive_nodes4_ch(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+                                             ctx->pairs_ch.as<float4>(), ctx->nodes4_ch.as<float4>(), ctx->stream);
+        ctx->nodes4_ch_built = true;
+    }
     const size_t scene_bytes = (size_t)n_inner * 64u + n_models * 20u;
     if (env_int("BVR_NO_Q16", 0) || scene_bytes <= 160u * 1024u || n_inner > (1u << 20) || n_models > (1u << 20) || max_leaf > 1u)
         return BVR_OK;
@@ -276,7 +285,7 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->pairs_ch, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->nodes4_ch};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
@@ -536,6 +545,7 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     p.scene.spheres = ctx->spheres.as<float4>();
     p.scene.sphere_material = ctx->sphere_material.as<uint32_t>();
     p.scene.materials = ctx->raw_materials.as<float4>();
+    if (ctx->nodes4_ch_built && !env_int("BVR_NO_BVH4", 0)) p.scene.nodes4_ch = ctx->nodes4_ch.as<float4>();
     if (ctx->q16_built) {
         if (ctx->q16_pending) { BVR_CK(cudaEventSynchronize(ctx->q16_done)); ctx->q16_pending = false; }
         if (*ctx->q16_bad_host == 0u) {

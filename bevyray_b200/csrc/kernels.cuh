@@ -79,6 +79,11 @@ int launch_derive_pairs_q16(const RawNode* nodes, uint32_t n_nodes, const uint32
 int launch_derive_nodes4_q16(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, const uint4* pairs_q,
                              uint4* nodes4, cudaStream_t stream);
 
+// 112-byte 4-wide fp32 records for scenes staged in shared memory (needs <= 1024 inner nodes / models, one model
+// per leaf); after launch_derive_pairs
+int launch_derive_nodes4_ch(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, const float4* pairs_ch,
+                            float4* nodes4, cudaStream_t stream);
+
 // ---- GPU BVH builder (bvh_build.cu) ----
 size_t bvh_build_scratch_bytes(uint32_t n_models);
 int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, void* scratch, uint32_t** depth_out,

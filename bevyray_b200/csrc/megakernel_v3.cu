@@ -107,6 +107,26 @@ __device__ __forceinline__ bool box_cull_q16(uint32_t wx, uint32_t wy, uint32_t 
     return entry <= exit;
 }
 
+// Four children as packed keys (entry distance in the high bits, ref in the low bits; 0xffffffff = not entered):
+// sorts them with a 5-comparator network of integer min/max, parks the three farther ones (farthest first) and
+// returns the nearest.
+__device__ __forceinline__ uint32_t sort4_park(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t& sp_addr,
+                                               const uint32_t stride) {
+    uint32_t t0;
+    t0 = min(k0, k1); k1 = max(k0, k1); k0 = t0;
+    t0 = min(k2, k3); k3 = max(k2, k3); k2 = t0;
+    t0 = min(k0, k2); k2 = max(k0, k2); k0 = t0;
+    t0 = min(k1, k3); k3 = max(k1, k3); k1 = t0;
+    t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
+    if (k3 != 0xffffffffu) { sts32(sp_addr, k3); sp_addr += stride; }
+    if (k2 != 0xffffffffu) { sts32(sp_addr, k2); sp_addr += stride; }
+    if (k1 != 0xffffffffu) { sts32(sp_addr, k1); sp_addr += stride; }
+    return k0;
+}
+
+#define S4_LEAF 0x400u
+#define S4_NONE 0x800u
+#define S4_REF_MASK 0x7ffu
 #define Q16_LEAF 0x100000u
 #define Q16_NONE 0x200000u
 #define Q16_REF_MASK 0x1fffffu
@@ -120,14 +140,18 @@ struct Tuning {
 // stack entries.  MODE 2: scene in HBM/L2, 32-byte quantised records (one 256-bit load per visit), 4-byte stack
 // entries (11 bits of distance | 21 bits of child ref).  MODE 3: as 2, on the 64-byte 4-wide records (two 256-bit
 // loads issued together): two levels of the tree per dependent fetch, the children sorted as packed 32-bit keys.
+// MODE 4: scene in shared memory as 112-byte 4-wide fp32 records, refs in 11 bits, 4-byte stack entries (21 bits of
+// distance | 11 bits of ref): half as many traversal steps as MODE 0, so half the per-step overhead.
 template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, unsigned int* __restrict__ pixel_counter,
                                                          const uint32_t n_inner, const uint32_t n_models,
                                                          const Tuning tune) {
-    constexpr bool SMEM_SCENE = MODE == 0;
-    constexpr bool Q16 = MODE >= 2;
+    constexpr bool SMEM_SCENE = MODE == 0 || MODE == 4;
+    constexpr bool Q16 = MODE == 2 || MODE == 3;
     constexpr bool W4 = MODE == 3;
-    constexpr uint32_t NONE = Q16 ? Q16_NONE : V3_NONE;
+    constexpr bool S4 = MODE == 4;
+    constexpr bool STACK4 = Q16 || S4;        // 4-byte stack entries
+    constexpr uint32_t NONE = Q16 ? Q16_NONE : (S4 ? S4_NONE : V3_NONE);
     extern __shared__ float4 smem[];
     const CameraParams& cam = p.cam;
     const unsigned full = 0xffffffffu;
@@ -136,12 +160,13 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     SceneView sv = p.scene;
     float4* sm_cursor = smem;
     if (SMEM_SCENE) {
-        float4* sm_pairs = sm_cursor;     sm_cursor += 4u * n_inner;
+        const uint32_t rec4 = S4 ? 7u : 4u;   // float4 per inner node
+        float4* sm_pairs = sm_cursor;     sm_cursor += rec4 * n_inner;
         float4* sm_spheres = sm_cursor;   sm_cursor += n_models;
         float4* sm_materials = sm_cursor; sm_cursor += 2u * sv.n_materials;
         uint32_t* sm_matid = reinterpret_cast<uint32_t*>(sm_cursor);
         sm_cursor += (n_models + 3u) / 4u;
-        for (uint32_t i = tid; i < 4u * n_inner; i += THREADS) sm_pairs[i] = p.scene.pairs_ch[i];
+        for (uint32_t i = tid; i < rec4 * n_inner; i += THREADS) sm_pairs[i] = S4 ? p.scene.nodes4_ch[i] : p.scene.pairs_ch[i];
         for (uint32_t i = tid; i < n_models; i += THREADS) sm_spheres[i] = p.scene.spheres[i];
         for (uint32_t i = tid; i < 2u * sv.n_materials; i += THREADS) sm_materials[i] = p.scene.materials[i];
         for (uint32_t i = tid; i < n_models; i += THREADS) sm_matid[i] = p.scene.sphere_material[i];
@@ -152,14 +177,15 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         __syncthreads();
     }
     // per-lane stack: entry k of lane t at s_stack0 + k * STACK_STRIDE (interleaved: conflict-free)
-    constexpr uint32_t STACK_STRIDE = THREADS * (Q16 ? 4u : 8u);
-    const uint32_t s_stack0 = smem_addr(sm_cursor) + tid * (Q16 ? 4u : 8u);
+    constexpr uint32_t STACK_STRIDE = THREADS * (STACK4 ? 4u : 8u);
+    const uint32_t s_stack0 = smem_addr(sm_cursor) + tid * (STACK4 ? 4u : 8u);
     // MODE 2: the quantisation grid and the root in 21-bit form
     const float qbx = Q16 ? sv.qgrid[0] : 0.f, qby = Q16 ? sv.qgrid[1] : 0.f, qbz = Q16 ? sv.qgrid[2] : 0.f;
     const float qsx = Q16 ? sv.qgrid[4] : 0.f, qsy = Q16 ? sv.qgrid[5] : 0.f, qsz = Q16 ? sv.qgrid[6] : 0.f;
     const uint32_t root = !sv.has_scene ? NONE
                           : (Q16 ? ((sv.root_ref & BVR_LEAF_BIT) ? (Q16_LEAF | (sv.root_ref & 0xfffffu)) : sv.root_ref)
-                                 : sv.root_ref);
+                             : S4 ? ((sv.root_ref & BVR_LEAF_BIT) ? (S4_LEAF | (sv.root_ref & 0x3ffu)) : sv.root_ref)
+                                  : sv.root_ref);
     uint32_t snx = 0, sny = 0, snz = 0, sfx = 0, sfy = 0, sfz = 0;   // MODE 2: PRMT selectors of the near / far halves
     const uint32_t s_pairs = SMEM_SCENE ? smem_addr(sv.pairs_ch) : 0u;
 
@@ -384,11 +410,29 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             for (int rep = 0; rep < BVR_STEPS_PER_VOTE; rep++) {
                 if (state == TRAVERSE) {
                     uint32_t c = cur;
-                    if (Q16 ? c < Q16_LEAF : c < V3_NONE) {  // inner node: test both children
+                    if (Q16 ? c < Q16_LEAF : (S4 ? c < S4_LEAF : c < V3_NONE)) {  // inner node: test its children
                         uint32_t r0, r1;
                         float d0, d1;
                         bool h0, h1;
-                        if (W4) {
+                        if (S4) {
+                            // four children in shared memory: key = 21 bits of entry distance | 11 bits of ref
+                            const uint32_t na = s_pairs + c * 112u;
+                            const float4 q0 = lds128(na), q1 = lds128(na + 16u), q2 = lds128(na + 32u);
+                            const float4 q3 = lds128(na + 48u), q4 = lds128(na + 64u), q5 = lds128(na + 80u);
+                            const float4 rr = lds128(na + 96u);
+                            float e;
+                            uint32_t k0 = box_cull(inv, ainv, noi, closest.t, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, e)
+                                              ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.x)) : 0xffffffffu;
+                            uint32_t k1 = box_cull(inv, ainv, noi, closest.t, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, e)
+                                              ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.y)) : 0xffffffffu;
+                            uint32_t k2 = box_cull(inv, ainv, noi, closest.t, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, e)
+                                              ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.z)) : 0xffffffffu;
+                            uint32_t k3 = box_cull(inv, ainv, noi, closest.t, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, e)
+                                              ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.w)) : 0xffffffffu;
+                            k0 = sort4_park(k0, k1, k2, k3, sp_addr, STACK_STRIDE);
+                            c = k0 != 0xffffffffu ? (k0 & S4_REF_MASK) : NONE;
+                            r0 = r1 = 0u; d0 = d1 = 0.0f; h0 = h1 = false;
+                        } else if (W4) {
                             // four children: key = 11 bits of entry distance | 21 bits of ref, 0xffffffff = not entered
                             uint4 qa, qb, qc, qd;
                             const uint4* np = sv.nodes4_q + 4u * c;
@@ -403,16 +447,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                                               ? (((__float_as_uint(e) >> 20) << 21) | qc.w) : 0xffffffffu;
                             uint32_t k3 = box_cull_q16(qd.x, qd.y, qd.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
                                               ? (((__float_as_uint(e) >> 20) << 21) | qd.w) : 0xffffffffu;
-                            // sorting network, ascending
-                            uint32_t t0;
-                            t0 = min(k0, k1); k1 = max(k0, k1); k0 = t0;
-                            t0 = min(k2, k3); k3 = max(k2, k3); k2 = t0;
-                            t0 = min(k0, k2); k2 = max(k0, k2); k0 = t0;
-                            t0 = min(k1, k3); k3 = max(k1, k3); k1 = t0;
-                            t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
-                            if (k3 != 0xffffffffu) { sts32(sp_addr, k3); sp_addr += STACK_STRIDE; }
-                            if (k2 != 0xffffffffu) { sts32(sp_addr, k2); sp_addr += STACK_STRIDE; }
-                            if (k1 != 0xffffffffu) { sts32(sp_addr, k1); sp_addr += STACK_STRIDE; }
+                            k0 = sort4_park(k0, k1, k2, k3, sp_addr, STACK_STRIDE);
                             c = k0 != 0xffffffffu ? (k0 & Q16_REF_MASK) : NONE;
                             r0 = r1 = 0u; d0 = d1 = 0.0f; h0 = h1 = false;
                         } else if (Q16) {
@@ -439,7 +474,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                             h1 = box_cull(inv, ainv, noi, closest.t, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, d1);
                         }
                         const bool first0 = d0 < d1;         // ties go to the second child (reference LIFO order)
-                        if (W4) {
+                        if (W4 || S4) {
                         } else if (h0 && h1) {
                             if (Q16) {
                                 // far child: 11 bits of distance, rounded towards zero (conservative at pop time)
@@ -453,7 +488,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                             c = h0 ? r0 : (h1 ? r1 : NONE);
                         }
                     }
-                    if (Q16 ? (c & Q16_LEAF) != 0u : (int)c < 0) {   // leaf: park it, or wait for the batch test
+                    if (Q16 ? (c & Q16_LEAF) != 0u : (S4 ? (c & S4_LEAF) != 0u : (int)c < 0)) {   // leaf: park it, or wait for the batch test
                         if (pending == NONE) { pending = c; c = NONE; }
                         else blocked = true;
                     }
@@ -465,6 +500,9 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                             if (Q16) {
                                 const uint32_t e = lds32(sp_addr);
                                 if (__uint_as_float((e >> 21) << 20) < closest.t) { c = e & Q16_REF_MASK; break; }
+                            } else if (S4) {
+                                const uint32_t e = lds32(sp_addr);
+                                if (__uint_as_float(e & ~S4_REF_MASK) < closest.t) { c = e & S4_REF_MASK; break; }
                             } else {
                                 const uint2 e = lds64(sp_addr);
                                 if (__uint_as_float(e.y) < closest.t) { c = e.x; break; }
@@ -485,7 +523,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             const uint32_t nblk = (uint32_t)__popc(blk), ntrav = (uint32_t)__popc(trav);
             if (nblk >= tune.leaf_batch_lanes || nblk == ntrav) {
                 if (state == TRAVERSE && pending != NONE) {
-                    test_leaf(sv, ray, a, Q16 ? (pending & 0xfffffu) : pending, closest);
+                    test_leaf(sv, ray, a, Q16 ? (pending & 0xfffffu) : (S4 ? (pending & 0x3ffu) : pending), closest);
                     pending = NONE;
                 }
             }
@@ -507,8 +545,24 @@ template <int THREADS>
 int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
               unsigned int* pixel_counter, Tuning tune, int sm_count, cudaStream_t stream) {
     uint32_t stack_cap = tree_depth + 1u;
-    const size_t scene_bytes = (size_t)(4u * n_inner + n_models + 2u * p.scene.n_materials + (n_models + 3u) / 4u) * 16u;
+    size_t scene_bytes = (size_t)(4u * n_inner + n_models + 2u * p.scene.n_materials + (n_models + 3u) / 4u) * 16u;
     const size_t max_smem = 227u * 1024u;
+    // 4-wide fp32 records in shared memory when they and their 4-byte stacks fit
+    const uint32_t cap4 = 3u * ((tree_depth + 1u) / 2u) + 2u;
+    const size_t scene4_bytes = scene_bytes + (size_t)3u * n_inner * 16u;
+    const bool s4 = p.scene.nodes4_ch != nullptr && scene4_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t) <= max_smem;
+    if (s4) {
+        const size_t smem4 = scene4_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t);
+        auto k4 = megakernel_v3<THREADS, 4>;
+        if (cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4) != cudaSuccess) return -1;
+        const uint32_t tiles4 = ((p.cam.width + 7u) / 8u) * ((p.shard.rows + 3u) / 4u);
+        uint32_t grid4 = (uint32_t)sm_count;
+        const uint32_t useful4 = (tiles4 * 32u + THREADS - 1u) / THREADS;
+        if (grid4 > useful4) grid4 = useful4;
+        if (grid4 == 0) return 0;
+        k4<<<grid4, THREADS, smem4, stream>>>(p, pixel_counter, n_inner, n_models, tune);
+        return 1;
+    }
     const bool smem_scene = scene_bytes + (size_t)THREADS * stack_cap * sizeof(uint2) <= max_smem;
     const bool q16 = !smem_scene && p.scene.pairs_q != nullptr;   // quantised records qualify (bvr_api.cu)
     const bool w4 = q16 && p.scene.nodes4_q != nullptr;

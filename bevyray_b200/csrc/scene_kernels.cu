@@ -213,7 +213,53 @@ __global__ void build_nodes4_q16_kernel(const RawNode* __restrict__ nodes, uint3
     }
 }
 
+// pass 4d: 4-wide fp32 records for scenes staged in shared memory (megakernel_v3.cu MODE 4): 112 bytes per inner
+// node = four child boxes as (centre, half extent) + four refs in 11-bit form (bit 10 = leaf, bits 0-9 = inner
+// record / only model of the leaf; 0x800 = empty slot, whose negative half extent is never entered).
+__global__ void build_nodes4_ch_kernel(const RawNode* __restrict__ nodes, uint32_t n,
+                                       const uint32_t* __restrict__ inner_id, const float4* __restrict__ pairs_ch,
+                                       float4* __restrict__ nodes4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RawNode nd = nodes[i];
+    if (nd.model_count != 0u) return;
+    const uint32_t id = inner_id[i];
+    float box[4][6];
+    uint32_t ref[4];
+    auto take = [&](int slot, uint32_t rec, uint32_t which) {   // child `which` of pair record `rec`
+        const float4 q0 = pairs_ch[4u * rec], q1 = pairs_ch[4u * rec + 1u], q2 = pairs_ch[4u * rec + 2u], q3 = pairs_ch[4u * rec + 3u];
+        if (which == 0u) { box[slot][0] = q0.x; box[slot][1] = q0.y; box[slot][2] = q0.z; box[slot][3] = q0.w; box[slot][4] = q1.x; box[slot][5] = q1.y; }
+        else { box[slot][0] = q1.z; box[slot][1] = q1.w; box[slot][2] = q2.x; box[slot][3] = q2.y; box[slot][4] = q2.z; box[slot][5] = q2.w; }
+        const uint32_t r = __float_as_uint(which == 0u ? q3.x : q3.y);
+        ref[slot] = (r & BVR_LEAF_BIT) ? (0x400u | (r & 0x3ffu)) : r;
+    };
+#pragma unroll
+    for (uint32_t s = 0; s < 2u; s++) {
+        const uint32_t x = nd.index + s;
+        if (nodes[x].model_count > 0u) {
+            take(2 * s, id, s);
+            for (int k = 0; k < 3; k++) { box[2 * s + 1][k] = 0.0f; box[2 * s + 1][3 + k] = -1.0f; }
+            ref[2 * s + 1] = 0x800u;
+        } else {
+            take(2 * s, inner_id[x], 0u);
+            take(2 * s + 1, inner_id[x], 1u);
+        }
+    }
+    float4* out = nodes4 + 7u * id;
+    const float* b = &box[0][0];
+#pragma unroll
+    for (int k = 0; k < 6; k++) out[k] = make_float4(b[4 * k], b[4 * k + 1], b[4 * k + 2], b[4 * k + 3]);
+    out[6] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float(ref[2]), __uint_as_float(ref[3]));
+}
+
 }  // namespace
+
+int launch_derive_nodes4_ch(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, const float4* pairs_ch,
+                            float4* nodes4, cudaStream_t stream) {
+    if (n_nodes == 0) return 0;
+    build_nodes4_ch_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(nodes, n_nodes, inner_id, pairs_ch, nodes4);
+    return 1;
+}
 
 int launch_derive_nodes4_q16(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, const uint4* pairs_q,
                              uint4* nodes4, cudaStream_t stream) {

@@ -30,6 +30,7 @@ struct SceneView {
     const float4* __restrict__ pairs;            // 4 x float4 per inner node: child boxes as (min, max)
     const float4* __restrict__ pairs_ch;         // same records with the boxes as (centre, half extent):
                                                  //   q0 = (c0.xyz, h0.x) q1 = (h0.yz, c1.xy) q2 = (c1.z, h1.xyz) q3 = refs
+    const float4* __restrict__ nodes4_ch;        // 7 x float4 per inner node: 4-wide fp32 records (small scenes), or null
     const uint4* __restrict__ pairs_q;           // 32-byte records on a 16-bit grid (scene_kernels.cu), or null
     const uint4* __restrict__ nodes4_q;          // 64-byte 4-wide records on the same grid, or null
     const float* __restrict__ qgrid;             // (base.xyz, -, step.xyz, -) of that grid
