@@ -670,7 +670,7 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
                 if (variant != 2)
                     n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
                                              ctx->pixel_counter.as<unsigned int>(), threads,
-                                             (uint32_t)env_int("BVR_MK_WAIT", 26), (uint32_t)env_int("BVR_MK_LEAF", 4),
+                                             (uint32_t)env_int("BVR_MK_WAIT", 0), (uint32_t)env_int("BVR_MK_LEAF", 0),   // 0 = per-mode default
                                              ctx->sm_count, ctx->stream);
                 else
                     n = launch_megakernel_persistent(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,

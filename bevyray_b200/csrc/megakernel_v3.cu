@@ -552,6 +552,9 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
     const size_t scene4_bytes = scene_bytes + (size_t)3u * n_inner * 16u;
     const bool s4 = p.scene.nodes4_ch != nullptr && scene4_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t) <= max_smem;
     if (s4) {
+        // tuned on C2 (profiles/r01_tuning_sweeps.txt): the 4-wide walk wants later shading and immediate leaf tests
+        if (tune.shade_wait_lanes == 0u) tune.shade_wait_lanes = 29u;
+        if (tune.leaf_batch_lanes == 0u) tune.leaf_batch_lanes = 1u;
         const size_t smem4 = scene4_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t);
         auto k4 = megakernel_v3<THREADS, 4>;
         if (cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4) != cudaSuccess) return -1;
@@ -566,6 +569,10 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
     const bool smem_scene = scene_bytes + (size_t)THREADS * stack_cap * sizeof(uint2) <= max_smem;
     const bool q16 = !smem_scene && p.scene.pairs_q != nullptr;   // quantised records qualify (bvr_api.cu)
     const bool w4 = q16 && p.scene.nodes4_q != nullptr;
+    // scenes walked in HBM/L2 are latency bound: long rays, so lanes must not wait long for shading (C4: 26 -> 8
+    // lanes is 622 -> 414 ms, profiles/r01_tuning_sweeps.txt)
+    if (tune.shade_wait_lanes == 0u) tune.shade_wait_lanes = smem_scene ? 26u : 8u;
+    if (tune.leaf_batch_lanes == 0u) tune.leaf_batch_lanes = smem_scene ? 4u : 1u;
     if (w4) stack_cap = 3u * ((tree_depth + 1u) / 2u) + 2u;       // up to three siblings parked per 4-wide level
     const size_t stack_bytes = (size_t)THREADS * stack_cap * (q16 ? sizeof(uint32_t) : sizeof(uint2));
     const size_t smem = (smem_scene ? scene_bytes : 0) + stack_bytes;

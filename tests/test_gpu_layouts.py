@@ -1,0 +1,98 @@
+"""Every node layout / kernel variant of the megakernel against the oracle (bit-exact).  The variants are picked by
+the library from the scene; the environment knobs below force the others for A/B runs:
+  small scenes (staged in shared memory): 4-wide fp32 records (default), child-pair records (BVR_NO_BVH4),
+      two paths per lane (BVR_MK_VARIANT=4), unstaged v2 (BVR_MK_VARIANT=2), one thread per pixel (BVR_MK_V1);
+  big scenes (walked in HBM/L2): 4-wide 16-bit records (default), 2-wide 16-bit records (BVR_NO_BVH4),
+      fp32 child-pair records (BVR_NO_Q16, chosen at upload)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KNOBS = ("BVR_NO_BVH4", "BVR_NO_Q16", "BVR_MK_VARIANT", "BVR_MK_V1", "BVR_MK_THREADS")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.fixture
+def knobs():
+    saved = {k: os.environ.pop(k, None) for k in KNOBS}
+
+    def set_(**kw):
+        for k in KNOBS:
+            os.environ.pop(k, None)
+        os.environ.update({k: str(v) for k, v in kw.items()})
+    yield set_
+    for k in KNOBS:
+        os.environ.pop(k, None)
+        if saved[k] is not None:
+            os.environ[k] = saved[k]
+
+
+def check(got, want, cnt, stats, tag):
+    for k in ("primary_id", "primary_depth", "rt_depth", "rgba"):
+        assert np.array_equal(bits(got[k]), bits(want[k])), (tag, k)
+    assert stats["rays"] == cnt["rays"], tag
+
+
+SMALL = [dict(), dict(BVR_NO_BVH4=1), dict(BVR_MK_VARIANT=4), dict(BVR_MK_VARIANT=2), dict(BVR_MK_V1=1),
+         dict(BVR_MK_THREADS=512), dict(BVR_NO_BVH4=1, BVR_MK_THREADS=768)]
+
+
+@pytest.mark.parametrize("env", SMALL, ids=lambda e: "-".join(f"{k[4:]}={v}" for k, v in e.items()) or "default")
+def test_small_scene_layouts(bvr, oracle, ctx, rtiow, knobs, env):
+    """RTIOW final scene (506 spheres, in shared memory), book camera, 10 bounces, ragged image size."""
+    W, H = 333, 187
+    cam = bvr.make_camera(position=(13, 2, 3), target=(0, 0, 0), fov=float(np.deg2rad(20)), aspect=W / H,
+                          sample_count=5, bounces=10)
+    win = bvr.make_window(0.37, H)
+    want, cnt = oracle.render(rtiow.models, rtiow.materials, rtiow.nodes, cam, bvr.make_level(3), win, W)
+    knobs(**env)
+    ctx.upload_scene(rtiow.models, rtiow.materials, rtiow.nodes)
+    got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
+    check(got, want, cnt, ctx.stats(), env)
+
+
+@pytest.mark.parametrize("gpu_bvh", [False, True], ids=["host-ploc", "gpu-lbvh"])
+@pytest.mark.parametrize("env", [dict(), dict(BVR_NO_BVH4=1), dict(BVR_NO_Q16=1), dict(BVR_MK_THREADS=768)],
+                         ids=lambda e: "-".join(f"{k[4:]}={v}" for k, v in e.items()) or "default")
+def test_big_scene_layouts(bvr, oracle, ctx, knobs, env, gpu_bvh):
+    """30k random spheres (C4's density): the records live in HBM/L2.  Also through the GPU-built tree, whose
+    nodes are read back and handed to the oracle."""
+    scene = bvr.Scene.random(3, 30000, 62.0, 0.05, 0.25)
+    W, H = 200, 120
+    cam = bvr.make_camera(position=(0, 0, 42), target=(0, 0, 0), aspect=W / H, sample_count=2, bounces=8)
+    win = bvr.make_window(0.81, H)
+    knobs(**env)
+    if gpu_bvh:
+        nodes = ctx.upload_scene_gpu_bvh(scene.models, scene.materials, want_nodes=True)
+        assert bvr.validate_bvh(nodes, scene.models) is None
+    else:
+        nodes = scene.nodes
+        ctx.upload_scene(scene.models, scene.materials, nodes)
+    got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
+    want, cnt = oracle.render(scene.models, scene.materials, nodes, cam, bvr.make_level(3), win, W)
+    assert cnt["stack_truncations"] == 0
+    check(got, want, cnt, ctx.stats(), (env, gpu_bvh))
+
+
+def test_quantised_records_refuse_boxes_outside_the_root(bvr, oracle, ctx, knobs):
+    """A child box that pokes out of the root box cannot be put on the root's 16-bit grid without shrinking it:
+    the library must notice and fall back to the fp32 records (same image as the oracle either way)."""
+    scene = bvr.Scene.random(5, 6000, 36.0, 0.05, 0.25)
+    nodes = scene.nodes.copy()
+    inner = np.nonzero(nodes["model_count"] == 0)[0]
+    victim = int(nodes["index"][inner[len(inner) // 2]])
+    nodes["bounds_max"][victim] += np.float32(500.0)          # still conservative, but outside the root box
+    W, H = 160, 100
+    cam = bvr.make_camera(position=(0, 0, 26), target=(0, 0, 0), aspect=W / H, sample_count=2, bounces=6)
+    win = bvr.make_window(0.5, H)
+    knobs()
+    ctx.upload_scene(scene.models, scene.materials, nodes)
+    got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
+    want, cnt = oracle.render(scene.models, scene.materials, nodes, cam, bvr.make_level(3), win, W)
+    check(got, want, cnt, ctx.stats(), "box outside the root")

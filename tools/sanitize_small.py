@@ -25,7 +25,23 @@ for kernel, traversal, name in [(1, 0, "megakernel"), (1, 1, "reference-order"),
 nodes = ctx.upload_scene_gpu_bvh(scene.models, scene.materials, want_nodes=True)
 out = ctx.render(cam, 3, win, bvr.make_options(W))
 print("gpu-bvh", bvr.validate_bvh(nodes, scene.models), all(np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)) for k in ref))
-big = bvr.Scene.random(7, 3000, 30.0, 0.05, 0.25)
-ctx.upload_scene(big.models, big.materials, big.nodes)
-ctx.render(cam, 3, win, bvr.make_options(W))
+# megakernel variants chosen through the environment (tests/test_gpu_layouts.py)
+ctx.upload_scene(scene.models, scene.materials, scene.nodes)
+for env in ({"BVR_NO_BVH4": "1"}, {"BVR_MK_VARIANT": "4"}, {"BVR_MK_VARIANT": "2"}):
+    os.environ.update(env)
+    out = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
+    for k in env:
+        del os.environ[k]
+    print(env, all(np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)) for k in ref))
+# scenes walked in HBM/L2: 4-wide 16-bit records, 2-wide 16-bit records, fp32 records
+big = bvr.Scene.random(7, 6000, 36.0, 0.05, 0.25)
+bref = None
+for env in ({}, {"BVR_NO_BVH4": "1"}, {"BVR_NO_Q16": "1"}):
+    os.environ.update(env)
+    ctx.upload_scene(big.models, big.materials, big.nodes)
+    out = ctx.render(cam, 3, win, bvr.make_options(W))
+    for k in env:
+        del os.environ[k]
+    bref = bref or out
+    print("big", env, all(np.array_equal(out[k].view(np.uint32), bref[k].view(np.uint32)) for k in bref))
 print("done")
