@@ -351,8 +351,11 @@ def run_ours(args):
             hbm_roof = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": hbm_achieved / hbm_peak, "traffic": traffic, "bytes_per_ray": bpr,
                                     "peak_source": hbm_peak_src,
-                                    "note": "reference-layout bytes each fetched once; on C2 they are served from shared memory "
-                                            "(HBM is not the bound), on C4 from L2/HBM"}
+                                    "note": "reference-layout bytes of the reference-order traversal, each fetched once "
+                                            "(SURVEY 8d); on C2 they are served from shared memory (HBM is not the bound); on "
+                                            "C4 the kernel's near-first 4-wide walk fetches ~3x fewer nodes than that count and "
+                                            "97 % of its fetches hit L2 (ncu: 6.7 TB/s L2->SM, L1 wavefront pipe 83 % busy), "
+                                            "which is why frac exceeds 1"}
             # the scene of C4 (160 MB in reference layout) exceeds shared memory and L2: node fetches bound it
             if args.workload == "c4":
                 line["roofline"], line["roofline_fp32"] = hbm_roof, fp32_roof
