@@ -196,6 +196,14 @@ __global__ void bb_emit(const RawModel* __restrict__ models, const uint32_t* __r
     }
 }
 
+// Position of every model in the reference's traversal order (raytrace.wgsl:329-341 pushes child `index` first and
+// pops `index+1` first: right subtree before left).  Left children cover the lower part of the sorted range, so
+// the reference reaches the leaves in DESCENDING sorted position.
+__global__ void bb_rank(const uint32_t* __restrict__ sorted_model, uint32_t n, uint32_t* __restrict__ model_rank) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) model_rank[sorted_model[p]] = n - 1u - p;
+}
+
 __global__ void bb_single_leaf(const RawModel* __restrict__ models, RawNode* __restrict__ out, uint32_t* depth_out) {
     float4 lo, hi;
     leaf_box(models, 0u, lo, hi);
@@ -253,9 +261,10 @@ size_t bvh_build_scratch_bytes(uint32_t n_models) {
 }
 
 // Builds the node array for `n` models (device pointers) into `out_nodes` (2n-1 records).  `depth_out` is a
-// device word that receives the number of tree levels.  Returns the number of kernels launched, -1 on error.
-int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, void* scratch, uint32_t** depth_out,
-                     cudaStream_t stream) {
+// device word that receives the number of tree levels; `model_rank` (n words) receives every model's position in
+// the reference's traversal order (the tie-break of trace.cuh: test_leaf).  Returns the number of kernels launched, -1 on error.
+int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, uint32_t* model_rank, void* scratch,
+                     uint32_t** depth_out, cudaStream_t stream) {
     if (n == 0) return 0;
     size_t cub_bytes = cub_temp_bytes(n);
     const Layout L = make_layout(n, cub_bytes);
@@ -277,6 +286,7 @@ int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, voi
     int launches = 0;
     if (n == 1) {
         bb_single_leaf<<<1, 1, 0, stream>>>(models, out_nodes, depth);
+        cudaMemsetAsync(model_rank, 0, sizeof(uint32_t), stream);
         return 1;
     }
     const int T = 256;
@@ -294,7 +304,8 @@ int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, voi
     bb_fit<<<blocks, T, 0, stream>>>(models, vals_sorted, (int)n, children, parent_inner, parent_leaf, flags, box_lo, box_hi,
                                      height, depth);
     bb_emit<<<blocks, T, 0, stream>>>(models, vals_sorted, (int)n, children, box_lo, box_hi, out_nodes);
-    launches += 3;
+    bb_rank<<<blocks, T, 0, stream>>>(vals_sorted, n, model_rank);
+    launches += 4;
     return launches;
 }
 

@@ -59,8 +59,11 @@ struct BvrContext {
     // scene, reference layout (raw bytes in HBM) and the derived traversal layout
     DeviceBuffer raw_models, raw_materials, raw_nodes;
     DeviceBuffer spheres, sphere_material, pairs, pairs_ch, inner_id, block_sums, root_ref;
+    DeviceBuffer model_rank;                  // position of every model in the reference's traversal order
     DeviceBuffer nodes4_ch;                   // 4-wide fp32 records (scenes staged in shared memory)
     bool nodes4_ch_built = false;
+    DeviceBuffer raw_nodes_tight, pairs_tight, pairs_ch_tight, nodes4_tight, tight_groups;   // tight-box variant
+    bool tight_built = false;
     DeviceBuffer pairs_q, nodes4_q, qgrid;              // 32-byte quantised records + their grid (big scenes), flag at qgrid[8]
     unsigned int* q16_bad_host = nullptr;     // pinned copy of the 'does not qualify' flag
     bool q16_built = false, q16_pending = false;
@@ -140,11 +143,13 @@ uint32_t shard_rows_impl(uint32_t height, const BvrRenderOptions* o) {
 // Also yields the tree depth (stack bound for the near-first traversal).
 int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, size_t n_materials,
                    const BvrBvhNode* nodes, size_t n_nodes, uint32_t* depth_out, uint32_t* n_inner_out,
-                   uint32_t* max_leaf_out) {
+                   uint32_t* max_leaf_out, std::vector<uint32_t>* rank_out) {
     (void)models;
     *depth_out = 0;
     *n_inner_out = 0;
     *max_leaf_out = 0;
+    rank_out->assign(n_models, 0xffffffffu);
+    uint32_t next_rank = 0;
     if (n_models > 0 && n_materials == 0) return fail(ctx, BVR_ERR_BAD_SCENE, "models without materials");
     if (n_models >= (size_t)BVR_LEAF_FIRST_MASK) return fail(ctx, BVR_ERR_BAD_SCENE, "more than 2^24-1 models");
     if (n_nodes == 0) return BVR_OK;
@@ -163,6 +168,9 @@ int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, siz
             if (nd.model_count > BVR_MAX_LEAF_COUNT) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf with more than 128 models");
             if ((size_t)nd.index + nd.model_count > n_models) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf model range out of bounds");
             if (nd.model_count > *max_leaf_out) *max_leaf_out = nd.model_count;
+            // this walk pops index+1 before index, like raytrace.wgsl:329-341: leaves come off in the reference's order
+            for (uint32_t m = nd.index; m < nd.index + nd.model_count; m++)
+                if ((*rank_out)[m] == 0xffffffffu) (*rank_out)[m] = next_rank++;
         } else {
             (*n_inner_out)++;
             if ((size_t)nd.index + 1 >= n_nodes) return fail(ctx, BVR_ERR_BAD_SCENE, "child index out of bounds");
@@ -203,6 +211,25 @@ int derive_q16(BvrContext* ctx, size_t n_models, size_t n_nodes, uint32_t n_inne
         *launches += launch_derive_nodes4_ch(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
                                              ctx->pairs_ch.as<float4>(), ctx->nodes4_ch.as<float4>(), ctx->stream);
         ctx->nodes4_ch_built = true;
+        // tight boxes: pad 0.01 instead of the reference's 0.1; rays that start too far from the spheres for
+        // the tight boxes to be safe walk the reference records (scene_kernels.cu)
+        ctx->tight_built = false;
+        if (!env_int("BVR_NO_TIGHT", 0) && n_nodes <= 2047u) {
+            BVR_CK(ctx->raw_nodes_tight.ensure(n_nodes * sizeof(RawNode)));
+            BVR_CK(ctx->pairs_tight.ensure(n_nodes * 2 * sizeof(float4)));
+            BVR_CK(ctx->pairs_ch_tight.ensure(n_nodes * 2 * sizeof(float4)));
+            BVR_CK(ctx->nodes4_tight.ensure((size_t)n_inner * 112u));
+            BVR_CK(ctx->tight_groups.ensure(33 * sizeof(float4)));
+            *launches += launch_derive_tight(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->spheres.as<float4>(),
+                                             (uint32_t)n_models, 1e-4f * (float)env_int("BVR_TIGHT_PAD", 100), ctx->tight_groups.as<float4>(),
+                                             ctx->raw_nodes_tight.as<RawNode>(), ctx->stream);
+            *launches += launch_derive_pairs(ctx->raw_nodes_tight.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+                                             ctx->block_sums.as<uint32_t>(), ctx->pairs_tight.as<float4>(),
+                                             ctx->pairs_ch_tight.as<float4>(), ctx->root_ref.as<uint32_t>(), ctx->stream);
+            *launches += launch_derive_nodes4_ch(ctx->raw_nodes_tight.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+                                                 ctx->pairs_ch_tight.as<float4>(), ctx->nodes4_tight.as<float4>(), ctx->stream);
+            ctx->tight_built = true;
+        }
     }
     const size_t scene_bytes = (size_t)n_inner * 64u + n_models * 20u;
     if (env_int("BVR_NO_Q16", 0) || scene_bytes <= 160u * 1024u || n_inner > (1u << 20) || n_models > (1u << 20) || max_leaf > 1u)
@@ -285,7 +312,7 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->pairs_ch, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->nodes4_ch};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
@@ -338,7 +365,8 @@ int bvr_upload_scene(BvrContext* ctx,
         return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty ranges given before any full upload");
 
     uint32_t depth = 0, n_inner = 0, max_leaf = 0;
-    int st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth, &n_inner, &max_leaf);
+    std::vector<uint32_t> rank;
+    int st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth, &n_inner, &max_leaf, &rank);
     if (st != BVR_OK) return st;
 
     // the ranges to copy
@@ -363,6 +391,7 @@ int bvr_upload_scene(BvrContext* ctx,
     BVR_CK(ctx->raw_nodes.ensure(n_nodes * sizeof(BvrBvhNode)));
     BVR_CK(ctx->spheres.ensure(n_models * sizeof(float4)));
     BVR_CK(ctx->sphere_material.ensure(n_models * sizeof(uint32_t)));
+    BVR_CK(ctx->model_rank.ensure(n_models * sizeof(uint32_t)));
     BVR_CK(ctx->pairs.ensure(n_nodes * 2 * sizeof(float4)));   // <= ceil(n/2) inner nodes x 64 B
     BVR_CK(ctx->pairs_ch.ensure(n_nodes * 2 * sizeof(float4)));
     BVR_CK(ctx->inner_id.ensure(n_nodes * sizeof(uint32_t)));
@@ -371,6 +400,7 @@ int bvr_upload_scene(BvrContext* ctx,
     // stage + copy
     size_t staging_bytes = 0;
     for (const Copy& c : copies) staging_bytes += ((c.count * strides[c.array]) + 255) & ~(size_t)255;
+    staging_bytes += (n_models * sizeof(uint32_t) + 255) & ~(size_t)255;   // model ranks
     if (ctx->upload_pending) { BVR_CK(cudaEventSynchronize(ctx->upload_done)); ctx->upload_pending = false; }
     BVR_CK(ctx->upload_staging.ensure(staging_bytes));
     BVR_CK(cudaEventRecord(ctx->ev_upload0, ctx->stream));
@@ -386,6 +416,11 @@ int bvr_upload_scene(BvrContext* ctx,
         if (st != BVR_OK) return st;
         if (c.array == BVR_ARRAY_MODELS) models_dirty = true;
         if (c.array == BVR_ARRAY_BVH_NODES) nodes_dirty = true;
+    }
+    if ((nodes_dirty || !partial) && n_models) {
+        // derived on the host from the node array (the walk above): 4 bytes per model travel with every new tree
+        st = h2d(ctx, ctx->model_rank.ptr, rank.data(), n_models * sizeof(uint32_t), ctx->upload_staging, off);
+        if (st != BVR_OK) return st;
     }
     BVR_CK(cudaEventRecord(ctx->upload_done, ctx->stream));
     ctx->upload_pending = true;
@@ -407,7 +442,7 @@ int bvr_upload_scene(BvrContext* ctx,
                                      : 0u;   // node 0 is the first inner node -> dense id 0
         }
     }
-    if (nodes_dirty || !partial) {
+    if (nodes_dirty || models_dirty || !partial) {
         st = derive_q16(ctx, n_models, n_nodes, n_inner, max_leaf, &launches);
         if (st != BVR_OK) return st;
     }
@@ -462,6 +497,7 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
     BVR_CK(ctx->raw_nodes.ensure(n_nodes * sizeof(BvrBvhNode)));
     BVR_CK(ctx->spheres.ensure(n_models * sizeof(float4)));
     BVR_CK(ctx->sphere_material.ensure(n_models * sizeof(uint32_t)));
+    BVR_CK(ctx->model_rank.ensure(n_models * sizeof(uint32_t)));
     BVR_CK(ctx->pairs.ensure(n_nodes * 2 * sizeof(float4)));
     BVR_CK(ctx->pairs_ch.ensure(n_nodes * 2 * sizeof(float4)));
     BVR_CK(ctx->inner_id.ensure(n_nodes * sizeof(uint32_t)));
@@ -489,7 +525,7 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
     *ctx->depth_host = 0;
     if (n_models) {
         const int nb = launch_bvh_build(ctx->raw_models.as<RawModel>(), (uint32_t)n_models, ctx->raw_nodes.as<RawNode>(),
-                                        ctx->bvh_scratch.ptr, &d_depth, ctx->stream);
+                                        ctx->model_rank.as<uint32_t>(), ctx->bvh_scratch.ptr, &d_depth, ctx->stream);
         if (nb < 0) return fail_cuda(ctx, cudaGetLastError(), "GPU BVH build");
         launches += nb;
         launches += launch_derive_spheres(ctx->raw_models.as<RawModel>(), (uint32_t)n_models, ctx->spheres.as<float4>(),
@@ -545,7 +581,14 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     p.scene.spheres = ctx->spheres.as<float4>();
     p.scene.sphere_material = ctx->sphere_material.as<uint32_t>();
     p.scene.materials = ctx->raw_materials.as<float4>();
-    if (ctx->nodes4_ch_built && !env_int("BVR_NO_BVH4", 0)) p.scene.nodes4_ch = ctx->nodes4_ch.as<float4>();
+    p.scene.model_rank = ctx->n_models ? ctx->model_rank.as<uint32_t>() : nullptr;
+    if (ctx->nodes4_ch_built && !env_int("BVR_NO_BVH4", 0)) {
+        p.scene.nodes4_ch = ctx->nodes4_ch.as<float4>();
+        if (ctx->tight_built && !env_int("BVR_NO_TIGHT", 0)) {
+            p.scene.nodes4_tight = ctx->nodes4_tight.as<float4>();
+            p.scene.tight_groups = ctx->tight_groups.as<float4>();
+        }
+    }
     if (ctx->q16_built) {
         if (ctx->q16_pending) { BVR_CK(cudaEventSynchronize(ctx->q16_done)); ctx->q16_pending = false; }
         if (*ctx->q16_bad_host == 0u) {

@@ -84,10 +84,14 @@ int launch_derive_nodes4_q16(const RawNode* nodes, uint32_t n_nodes, const uint3
 int launch_derive_nodes4_ch(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, const float4* pairs_ch,
                             float4* nodes4, cudaStream_t stream);
 
+// tight boxes (small scenes): see scene_kernels.cu
+int launch_derive_tight(const RawNode* nodes, uint32_t n_nodes, const float4* spheres, uint32_t n_models, float pad,
+                        float4* groups, RawNode* nodes_tight, cudaStream_t stream);
+
 // ---- GPU BVH builder (bvh_build.cu) ----
 size_t bvh_build_scratch_bytes(uint32_t n_models);
-int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, void* scratch, uint32_t** depth_out,
-                     cudaStream_t stream);
+int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, uint32_t* model_rank, void* scratch,
+                     uint32_t** depth_out, cudaStream_t stream);
 
 // ---- render kernels ----
 int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple one-thread-per-pixel kernel (v1)

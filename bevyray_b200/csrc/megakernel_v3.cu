@@ -142,14 +142,18 @@ struct Tuning {
 // loads issued together): two levels of the tree per dependent fetch, the children sorted as packed 32-bit keys.
 // MODE 4: scene in shared memory as 112-byte 4-wide fp32 records, refs in 11 bits, 4-byte stack entries (21 bits of
 // distance | 11 bits of ref): half as many traversal steps as MODE 0, so half the per-step overhead.
+// MODE 5: as 4, with the TIGHT-box records in shared memory (scene_kernels.cu): fewer node visits and sphere
+// tests; a ray whose origin is too far from some radius group for the tight boxes to be safe reads the reference
+// records from HBM/L2 instead (same code, different loads).
 template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, unsigned int* __restrict__ pixel_counter,
                                                          const uint32_t n_inner, const uint32_t n_models,
                                                          const Tuning tune) {
-    constexpr bool SMEM_SCENE = MODE == 0 || MODE == 4;
+    constexpr bool SMEM_SCENE = MODE == 0 || MODE == 4 || MODE == 5;
+    constexpr bool TIGHT = MODE == 5;
     constexpr bool Q16 = MODE == 2 || MODE == 3;
     constexpr bool W4 = MODE == 3;
-    constexpr bool S4 = MODE == 4;
+    constexpr bool S4 = MODE == 4 || MODE == 5;
     constexpr bool STACK4 = Q16 || S4;        // 4-byte stack entries
     constexpr uint32_t NONE = Q16 ? Q16_NONE : (S4 ? S4_NONE : V3_NONE);
     extern __shared__ float4 smem[];
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         float4* sm_materials = sm_cursor; sm_cursor += 2u * sv.n_materials;
         uint32_t* sm_matid = reinterpret_cast<uint32_t*>(sm_cursor);
         sm_cursor += (n_models + 3u) / 4u;
-        for (uint32_t i = tid; i < rec4 * n_inner; i += THREADS) sm_pairs[i] = S4 ? p.scene.nodes4_ch[i] : p.scene.pairs_ch[i];
+        for (uint32_t i = tid; i < rec4 * n_inner; i += THREADS) sm_pairs[i] = TIGHT ? p.scene.nodes4_tight[i] : (S4 ? p.scene.nodes4_ch[i] : p.scene.pairs_ch[i]);
         for (uint32_t i = tid; i < n_models; i += THREADS) sm_spheres[i] = p.scene.spheres[i];
         for (uint32_t i = tid; i < 2u * sv.n_materials; i += THREADS) sm_materials[i] = p.scene.materials[i];
         for (uint32_t i = tid; i < n_models; i += THREADS) sm_matid[i] = p.scene.sphere_material[i];
@@ -187,6 +191,8 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                              : S4 ? ((sv.root_ref & BVR_LEAF_BIT) ? (S4_LEAF | (sv.root_ref & 0x3ffu)) : sv.root_ref)
                                   : sv.root_ref);
     uint32_t snx = 0, sny = 0, snz = 0, sfx = 0, sfy = 0, sfz = 0;   // MODE 2: PRMT selectors of the near / far halves
+    const uint32_t n_groups = TIGHT ? __float_as_uint(__ldg(&sv.tight_groups[0]).x) : 0u;
+    bool far_ray = false;   // MODE 5: this ray walks the reference boxes
     const uint32_t s_pairs = SMEM_SCENE ? smem_addr(sv.pairs_ch) : 0u;
 
     const uint32_t tiles_x = (cam.width + 7u) / 8u, tiles_y = (p.shard.rows + 3u) / 4u;
@@ -393,6 +399,14 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
                 noi = v3(-(ray.o.x * inv.x), -(ray.o.y * inv.y), -(ray.o.z * inv.z));
             }
+            if constexpr (TIGHT) {
+                far_ray = false;
+                for (uint32_t g = 0; g < n_groups; g++) {
+                    const float4 gr = __ldg(&sv.tight_groups[1u + g]);
+                    const float dx = ray.o.x - gr.x, dy = ray.o.y - gr.y, dz = ray.o.z - gr.z;
+                    far_ray = far_ray || !(dx * dx + dy * dy + dz * dz <= gr.w);
+                }
+            }
             a = vdot(ray.d, ray.d);
             closest.t = BVR_INF;
             closest.model = 0xffffffffu;
@@ -417,9 +431,16 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                         if (S4) {
                             // four children in shared memory: key = 21 bits of entry distance | 11 bits of ref
                             const uint32_t na = s_pairs + c * 112u;
-                            const float4 q0 = lds128(na), q1 = lds128(na + 16u), q2 = lds128(na + 32u);
-                            const float4 q3 = lds128(na + 48u), q4 = lds128(na + 64u), q5 = lds128(na + 80u);
-                            const float4 rr = lds128(na + 96u);
+                            float4 q0, q1, q2, q3, q4, q5, rr;
+                            if (TIGHT && far_ray) {
+                                const float4* nd = sv.nodes4_ch + 7u * c;
+                                q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2); q3 = __ldg(nd + 3);
+                                q4 = __ldg(nd + 4); q5 = __ldg(nd + 5); rr = __ldg(nd + 6);
+                            } else {
+                                q0 = lds128(na); q1 = lds128(na + 16u); q2 = lds128(na + 32u);
+                                q3 = lds128(na + 48u); q4 = lds128(na + 64u); q5 = lds128(na + 80u);
+                                rr = lds128(na + 96u);
+                            }
                             float e;
                             uint32_t k0 = box_cull(inv, ainv, noi, closest.t, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, e)
                                               ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.x)) : 0xffffffffu;
@@ -551,12 +572,13 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
     const uint32_t cap4 = 3u * ((tree_depth + 1u) / 2u) + 2u;
     const size_t scene4_bytes = scene_bytes + (size_t)3u * n_inner * 16u;
     const bool s4 = p.scene.nodes4_ch != nullptr && scene4_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t) <= max_smem;
+    const bool tight = s4 && p.scene.nodes4_tight != nullptr;
     if (s4) {
         // tuned on C2 (profiles/r01_tuning_sweeps.txt): the 4-wide walk wants later shading and immediate leaf tests
         if (tune.shade_wait_lanes == 0u) tune.shade_wait_lanes = 29u;
         if (tune.leaf_batch_lanes == 0u) tune.leaf_batch_lanes = 1u;
         const size_t smem4 = scene4_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t);
-        auto k4 = megakernel_v3<THREADS, 4>;
+        auto k4 = tight ? megakernel_v3<THREADS, 5> : megakernel_v3<THREADS, 4>;
         if (cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4) != cudaSuccess) return -1;
         const uint32_t tiles4 = ((p.cam.width + 7u) / 8u) * ((p.shard.rows + 3u) / 4u);
         uint32_t grid4 = (uint32_t)sm_count;

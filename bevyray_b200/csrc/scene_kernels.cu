@@ -252,7 +252,129 @@ __global__ void build_nodes4_ch_kernel(const RawNode* __restrict__ nodes, uint32
     out[6] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float(ref[2]), __uint_as_float(ref[3]));
 }
 
+// ---- tight boxes for scenes staged in shared memory ----------------------------------------------
+// The reference pads every sphere box by 0.1 (extract.rs:220-227).  A hit needs disc >= 0 in hit_sphere's f32
+// arithmetic; with L = |origin - centre| the rounding error of disc is below ERR * L^2 * |d|^2, so such a ray
+// passes within sqrt(r^2 + ERR * L^2) of the centre: a box padded by `pad` cannot lose the hit as long as
+// ERR * L^2 <= 2 r pad + pad^2.  Spheres are grouped by radius octave; per group the kernel emits the bounding
+// ball (C, R) of the centres and the squared distance D2 = (sqrt((2 rmin pad + pad^2) / ERR) - R)^2 inside which a
+// ray origin satisfies that bound for every sphere of the group.  A ray whose origin lies outside any group's
+// ball ("far") walks the reference boxes instead.  ERR = 4 x 18 x 2^-24 (18 roundings on the way to disc, x4).
+__device__ __forceinline__ uint32_t ordered_bits(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__global__ void tight_groups_kernel(const float4* __restrict__ spheres, uint32_t n, float pad, float err,
+                                    float4* __restrict__ groups_out) {
+    __shared__ uint32_t lo[32][3], hi[32][3], rmin[32];
+    __shared__ uint32_t bad;
+    const uint32_t tid = threadIdx.x;
+    if (tid < 32u) {
+        for (int k = 0; k < 3; k++) { lo[tid][k] = 0xffffffffu; hi[tid][k] = 0u; }
+        rmin[tid] = 0x7f800000u;
+    }
+    if (tid == 0u) bad = 0u;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+        const float4 sp = spheres[i];
+        const float r = fabsf(sp.w);
+        if (!(r < 3.0e38f) || !(fabsf(sp.x) < 3.0e38f) || !(fabsf(sp.y) < 3.0e38f) || !(fabsf(sp.z) < 3.0e38f)) { bad = 1u; continue; }
+        int g = (int)(__float_as_uint(r) >> 23) - 127 + 16;
+        g = g < 0 ? 0 : (g > 31 ? 31 : g);
+        atomicMin(&lo[g][0], ordered_bits(sp.x)); atomicMax(&hi[g][0], ordered_bits(sp.x));
+        atomicMin(&lo[g][1], ordered_bits(sp.y)); atomicMax(&hi[g][1], ordered_bits(sp.y));
+        atomicMin(&lo[g][2], ordered_bits(sp.z)); atomicMax(&hi[g][2], ordered_bits(sp.z));
+        atomicMin(&rmin[g], __float_as_uint(r));
+    }
+    __syncthreads();
+    if (tid < 32u) {
+        float4 out = make_float4(0.f, 0.f, 0.f, -1.0f);
+        const bool used = rmin[tid] != 0x7f800000u;
+        if (used) {
+            float c[3], ext2 = 0.0f;
+            for (int k = 0; k < 3; k++) {
+                const float a = from_ordered_bits(lo[tid][k]), b = from_ordered_bits(hi[tid][k]);
+                c[k] = 0.5f * (a + b);
+                const float h = 0.5f * (b - a);
+                ext2 += h * h;
+            }
+            const float R = sqrtf(ext2) * 1.0001f + 1e-6f;
+            const float rm = __uint_as_float(rmin[tid]);
+            const float D = sqrtf((2.0f * rm * pad + pad * pad) / err) * 0.999f - R;
+            out = make_float4(c[0], c[1], c[2], (bad == 0u && D > 0.0f) ? D * D : -1.0f);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, used);
+        if (used) groups_out[1 + __popc(m & ((1u << tid) - 1u))] = out;
+        if (tid == 0u) groups_out[0] = make_float4(__uint_as_float((uint32_t)__popc(m)), 0.f, 0.f, 0.f);
+    }
+}
+
+// Copy of the node array with every box shrunk to (union of its spheres padded by `pad`) ∩ (uploaded box): one CTA,
+// bottom-up by rounds (at most 2047 nodes).
+__global__ void tight_refit_kernel(const RawNode* __restrict__ nodes, uint32_t n, const float4* __restrict__ spheres,
+                                   float pad, RawNode* __restrict__ out) {
+    __shared__ unsigned char done[2048];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+        RawNode nd = nodes[i];
+        done[i] = 0;
+        if (nd.model_count > 0u) {
+            float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+            for (uint32_t m = nd.index; m < nd.index + nd.model_count; m++) {
+                const float4 sp = spheres[m];
+                const float e = __fadd_ru(fabsf(sp.w), pad);
+                const float c[3] = {sp.x, sp.y, sp.z};
+                for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], __fsub_rd(c[k], e)); mx[k] = fmaxf(mx[k], __fadd_ru(c[k], e)); }
+            }
+            for (int k = 0; k < 3; k++) { nd.mn[k] = fmaxf(nd.mn[k], mn[k]); nd.mx[k] = fminf(nd.mx[k], mx[k]); }
+            done[i] = 1;
+        }
+        out[i] = nd;
+    }
+    __syncthreads();
+    for (int round = 0; round < 2048; round++) {
+        bool progress = false;
+        uint32_t mine[2] = {0xffffffffu, 0xffffffffu};
+        int k2 = 0;
+        for (uint32_t i = tid; i < n; i += blockDim.x, k2++) {
+            if (done[i]) continue;
+            const RawNode nd = nodes[i];
+            const uint32_t c0 = nd.index, c1 = nd.index + 1u;
+            if (c1 < n && done[c0] && done[c1]) {
+                const RawNode a = out[c0], b = out[c1];
+                RawNode o = nd;
+                for (int k = 0; k < 3; k++) {
+                    o.mn[k] = fmaxf(nd.mn[k], fminf(a.mn[k], b.mn[k]));
+                    o.mx[k] = fminf(nd.mx[k], fmaxf(a.mx[k], b.mx[k]));
+                }
+                out[i] = o;
+                if (k2 < 2) mine[k2] = i;
+                progress = true;
+            }
+        }
+        const int any = __syncthreads_or(progress ? 1 : 0);
+        for (int k = 0; k < 2; k++) if (mine[k] != 0xffffffffu) done[mine[k]] = 1;
+        __syncthreads();
+        if (!any) break;
+    }
+}
+
 }  // namespace
+
+// Tight variant of the small-scene records: groups (33 float4: count, then (C.xyz, D2) per group), the refitted node
+// copy, and from it the usual derived records.  Caller guarantees n_nodes <= 2047.
+int launch_derive_tight(const RawNode* nodes, uint32_t n_nodes, const float4* spheres, uint32_t n_models, float pad,
+                        float4* groups, RawNode* nodes_tight, cudaStream_t stream) {
+    if (n_nodes == 0 || n_nodes > 2047u) return 0;
+    const float err = 4.0f * 18.0f * 5.9604645e-8f;
+    tight_groups_kernel<<<1, 1024, 0, stream>>>(spheres, n_models, pad, err, groups);
+    tight_refit_kernel<<<1, 1024, 0, stream>>>(nodes, n_nodes, spheres, pad, nodes_tight);
+    return 2;
+}
 
 int launch_derive_nodes4_ch(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, const float4* pairs_ch,
                             float4* nodes4, cudaStream_t stream) {

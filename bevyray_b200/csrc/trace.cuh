@@ -31,12 +31,15 @@ struct SceneView {
     const float4* __restrict__ pairs_ch;         // same records with the boxes as (centre, half extent):
                                                  //   q0 = (c0.xyz, h0.x) q1 = (h0.yz, c1.xy) q2 = (c1.z, h1.xyz) q3 = refs
     const float4* __restrict__ nodes4_ch;        // 7 x float4 per inner node: 4-wide fp32 records (small scenes), or null
+    const float4* __restrict__ nodes4_tight;     // the same records with tight boxes (scene_kernels.cu), or null
+    const float4* __restrict__ tight_groups;     // [0].x = group count (bits), then (C.xyz, D2) per radius group
     const uint4* __restrict__ pairs_q;           // 32-byte records on a 16-bit grid (scene_kernels.cu), or null
     const uint4* __restrict__ nodes4_q;          // 64-byte 4-wide records on the same grid, or null
     const float* __restrict__ qgrid;             // (base.xyz, -, step.xyz, -) of that grid
     const float4* __restrict__ spheres;          // (centre.xyz, radius) per model
     const uint32_t* __restrict__ sphere_material;  // Model::material_id per model
     const float4* __restrict__ materials;        // 2 x float4 per material (reference bytes)
+    const uint32_t* __restrict__ model_rank;     // position of every model in the reference's traversal order, or null
     uint32_t root_ref;
     uint32_t n_materials;
     uint32_t has_scene;                          // 0: no nodes -> every ray misses
@@ -112,7 +115,15 @@ __device__ __forceinline__ void test_leaf(const SceneView& s, const Ray& ray, fl
         const float disc = fsub(fmul(h, h), fmul(a, c));
         if (disc < 0.0f) continue;                       // hit_sphere returns -1.0
         const float t = fdiv(fsub(h, fsqrt(disc)), a);
-        if (t != -1.0f && t > 0.001f && t < closest.t) { closest.t = t; closest.model = i; }
+        if (t != -1.0f && t > 0.001f) {
+            if (t < closest.t) { closest.t = t; closest.model = i; }
+            // Bit-exact tie between two spheres (a small sphere resting on the ground sphere, duplicates): the
+            // reference keeps the one it reaches FIRST (strict <, raytrace.wgsl:354), and its order over the
+            // leaves is fixed by the tree — right subtree first.  Any other visiting order reproduces that choice
+            // by preferring the lower rank.
+            else if (t == closest.t && i != closest.model && s.model_rank &&
+                     s.model_rank[i] < s.model_rank[closest.model]) closest.model = i;
+        }
     }
 }
 

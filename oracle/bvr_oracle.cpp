@@ -24,6 +24,8 @@
 //   * textureSample of the raster colour / depth at a pixel centre returns that texel.
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -118,6 +120,7 @@ struct Scene {
     BvrCamera camera; uint32_t level; BvrWindow window;
     float tan_half_fov;
     bool brute_force;
+    bool diagnose = false;   // BVRO_DIAGNOSE=1: cross-check every ray against a near-first traversal (debug aid)
 };
 
 // raytrace.wgsl:371-383
@@ -162,8 +165,76 @@ inline void raycast_against_range(const Scene& s, const Ray& ray, uint32_t start
     }
 }
 
+// Debug aid (BVRO_DIAGNOSE=1): the near-first, distance-culled traversal the CUDA kernels use, with the reference's
+// own box arithmetic.  Prints every ray on which it and the reference-order traversal disagree.
+inline void diagnose_near_first(const Scene& s, const Ray& ray, const HitInfo& ref) {
+    HitInfo closest{INF, v3(0, 0, 0), v3(0, 0, 0), 0u, true, 0xffffffffu};
+    Counters dummy;
+    struct E { uint32_t node; float d; };
+    std::vector<E> stack;
+    uint32_t cur = 0;
+    bool have = s.n_nodes > 0;
+    while (have) {
+        const BvrBvhNode& node = s.nodes[cur];
+        have = false;
+        if (node.model_count > 0) {
+            raycast_against_range(s, ray, node.index, node.model_count, closest, dummy);
+        } else {
+            const BvrBvhNode& n1 = s.nodes[node.index];
+            const BvrBvhNode& n2 = s.nodes[node.index + 1];
+            float d1 = ray_bounding_dst(ray, ld3(n1.bounds_min), ld3(n1.bounds_max));
+            float d2 = ray_bounding_dst(ray, ld3(n2.bounds_min), ld3(n2.bounds_max));
+            bool h1 = d1 != INF && d1 < closest.distance, h2 = d2 != INF && d2 < closest.distance;
+            if (h1 && h2) {
+                bool first1 = d1 < d2;
+                stack.push_back(first1 ? E{node.index + 1, d2} : E{node.index, d1});
+                cur = first1 ? node.index : node.index + 1; have = true;
+            } else if (h1) { cur = node.index; have = true; }
+            else if (h2) { cur = node.index + 1; have = true; }
+        }
+        while (!have && !stack.empty()) {
+            E e = stack.back(); stack.pop_back();
+            if (e.d < closest.distance) { cur = e.node; have = true; }
+        }
+    }
+    if (closest.model == ref.model && closest.distance == ref.distance) return;
+    std::fprintf(stderr, "DIAG ray o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g): reference hit model %u t=%.9g | near-first hit model %u t=%.9g\n",
+                 ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x, ray.direction.y, ray.direction.z,
+                 ref.model, ref.distance, closest.model, closest.distance);
+    // the chain of boxes above the reference's hit: node index, box distance
+    const uint32_t want = ref.model != 0xffffffffu ? ref.model : closest.model;
+    std::vector<uint32_t> path;
+    std::vector<std::pair<uint32_t, int>> dfs;   // node, depth
+    dfs.push_back({0u, 0});
+    std::vector<uint32_t> cur_path;
+    while (!dfs.empty()) {
+        auto [n, depth] = dfs.back(); dfs.pop_back();
+        cur_path.resize((size_t)depth); cur_path.push_back(n);
+        const BvrBvhNode& nd = s.nodes[n];
+        if (nd.model_count > 0) { if (want >= nd.index && want < nd.index + nd.model_count) { path = cur_path; break; } }
+        else { dfs.push_back({nd.index, depth + 1}); dfs.push_back({nd.index + 1, depth + 1}); }
+    }
+    for (uint32_t n : path) {
+        const BvrBvhNode& nd = s.nodes[n];
+        std::fprintf(stderr, "   node %u box dst %.9g  min=(%.6g %.6g %.6g) max=(%.6g %.6g %.6g)%s\n", n,
+                     ray_bounding_dst(ray, ld3(nd.bounds_min), ld3(nd.bounds_max)), nd.bounds_min[0], nd.bounds_min[1],
+                     nd.bounds_min[2], nd.bounds_max[0], nd.bounds_max[1], nd.bounds_max[2], nd.model_count ? " (leaf)" : "");
+    }
+    if (want != 0xffffffffu) {
+        const BvrModel& m = s.models[want];
+        std::fprintf(stderr, "   sphere %u c=(%.9g %.9g %.9g) r=%.9g hit_sphere=%.9g\n", want, m.position[0], m.position[1], m.position[2],
+                     m.radius, hit_sphere(m, ray));
+    }
+}
+
 // raytrace.wgsl:313-346
+inline HitInfo raycast_impl(const Scene& s, const Ray& ray, Counters& c);
 inline HitInfo raycast(const Scene& s, const Ray& ray, Counters& c) {
+    HitInfo h = raycast_impl(s, ray, c);
+    if (s.diagnose && !s.brute_force) diagnose_near_first(s, ray, h);
+    return h;
+}
+inline HitInfo raycast_impl(const Scene& s, const Ray& ray, Counters& c) {
     HitInfo closest{INF, v3(0, 0, 0), v3(0, 0, 0), 0u, true, 0xffffffffu};
     c.rays++;
     if (s.brute_force) {   // oracle-only: no BVH, every model tested in buffer order
@@ -367,6 +438,7 @@ int bvro_render(const BvrModel* models, size_t n_models,
     s.camera = *camera; s.level = level->level; s.window = *window;
     s.tan_half_fov = bvro_tan_half_fov(camera->fov);
     s.brute_force = brute_force != 0;
+    { const char* e = std::getenv("BVRO_DIAGNOSE"); s.diagnose = e && *e == '1'; }
     const uint32_t height = window->height;
     if (y1 > height) y1 = height;
     if ((s.level <= 2u) && (!raster_rgba || (s.level != 0u && !raster_depth))) return 1;

@@ -72,6 +72,9 @@ def render(models, materials, nodes, camera, level, window, width, raster_rgba=N
     models = np.ascontiguousarray(models)
     materials = np.ascontiguousarray(materials)
     nodes = np.ascontiguousarray(nodes)
+    # the reference's encase strides (extract.rs:181-237); numpy silently packs structured arrays in some operations
+    assert models.dtype.itemsize == 32 and materials.dtype.itemsize == 32 and nodes.dtype.itemsize == 48, \
+        "scene arrays must keep the 32/32/48-byte record layout"
     if raster_rgba is not None:
         raster_rgba = np.ascontiguousarray(raster_rgba, np.float32)
     if raster_depth is not None:

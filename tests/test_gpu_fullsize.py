@@ -39,6 +39,21 @@ def test_c2_full_frame_against_oracle_bands(bvr, oracle, ctx, rtiow):
     assert np.isfinite(rgb).all() and rgb.min() >= 0.0 and rgb.max() <= 1.0 + 1e-6 and np.all(got["rgba"][..., 3] == 1.0)
 
 
+def test_c2_whole_frame_against_oracle(bvr, oracle, ctx, rtiow):
+    """The benchmark frame itself — 1920x1080, 100 spp, 10 bounces, 516 M rays — every plane, every pixel, against
+    the oracle (about half a minute of CPU).  This is the frame on which a small sphere resting on the ground
+    produces a bit-exact tie in t at pixel (741, 412): see trace.cuh test_leaf."""
+    W, H = 1920, 1080
+    cam = book_camera(bvr, W, H, 100, 10)
+    win = bvr.make_window(0.37, H)
+    want, cnt = oracle.render(rtiow.models, rtiow.materials, rtiow.nodes, cam, bvr.make_level(3), win, W)
+    ctx.upload_scene(rtiow.models, rtiow.materials, rtiow.nodes)
+    got = ctx.render(cam, 3, win, bvr.make_options(W))
+    for k in ("primary_id", "primary_depth", "rt_depth", "rgba"):
+        assert np.array_equal(bits(got[k]), bits(want[k])), k
+    assert ctx.stats()["rays"] == cnt["rays"] == 515999699
+
+
 def test_c2_size_kernel_variants_and_shards_agree(bvr, ctx, rtiow):
     """Full 1080p frame at 8 spp: megakernel == reference-order == wavefront == CTA wavefront, and 8 tile
     shards reassemble to the same frame with the same total ray count."""

@@ -96,3 +96,49 @@ def test_quantised_records_refuse_boxes_outside_the_root(bvr, oracle, ctx, knobs
     got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
     want, cnt = oracle.render(scene.models, scene.materials, nodes, cam, bvr.make_level(3), win, W)
     check(got, want, cnt, ctx.stats(), "box outside the root")
+
+
+@pytest.mark.parametrize("gpu_bvh", [False, True], ids=["host-ploc", "gpu-lbvh"])
+@pytest.mark.parametrize("env", [dict(), dict(BVR_NO_TIGHT=1), dict(BVR_NO_BVH4=1), dict(BVR_MK_VARIANT=4), dict(BVR_MK_V1=1)],
+                         ids=lambda e: "-".join(f"{k[4:]}={v}" for k, v in e.items()) or "default")
+def test_exact_ties_go_to_the_sphere_the_reference_reaches_first(bvr, oracle, ctx, knobs, env, gpu_bvh):
+    """Two spheres with bit-identical t: the reference keeps the one it visits first (strict <, raytrace.wgsl:354),
+    and its visiting order is fixed by the tree.  Every sphere of this scene exists twice, with different materials,
+    so every hit is a tie; any visiting order must resolve it like the reference does (trace.cuh: model_rank)."""
+    rs = np.random.RandomState(11)
+    n = 120
+    base = np.zeros(n, bvr.MODEL_DTYPE)
+    base["position"] = rs.uniform(-4, 4, (n, 3)).astype(np.float32)
+    base["position"][:, 2] -= 9
+    base["radius"] = rs.uniform(0.2, 0.7, n).astype(np.float32)
+    models = np.zeros(2 * n, bvr.MODEL_DTYPE)      # (np.concatenate would pack the 32-byte records to 20 bytes)
+    models[:n], models[n:] = base, base
+    models = models[rs.permutation(2 * n)]
+    models["material_id"] = np.arange(2 * n)
+    mats = np.zeros(2 * n, bvr.MATERIAL_DTYPE)
+    mats["base_color"] = rs.uniform(0.1, 0.95, (2 * n, 3)).astype(np.float32)
+    mats["metallic"] = (rs.rand(2 * n) < 0.3).astype(np.float32)
+    mats["roughness"] = rs.uniform(0, 0.6, 2 * n).astype(np.float32)
+    mats["ior"] = 1.5
+    mats["specular_transmission"] = (rs.rand(2 * n) < 0.2).astype(np.float32)
+    W, H = 224, 126
+    cam = bvr.make_camera(position=(0, 0, 0), target=(0, 0, -1), aspect=W / H, sample_count=3, bounces=6)
+    win = bvr.make_window(0.29, H)
+    knobs(**env)
+    if gpu_bvh:
+        nodes = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
+    else:
+        nodes = bvr.build_ploc(models)
+        ctx.upload_scene(models, mats, nodes)
+    got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
+    want, cnt = oracle.render(models, mats, nodes, cam, bvr.make_level(3), win, W)
+    check(got, want, cnt, ctx.stats(), (env, gpu_bvh))
+    # the test means something only if ties are frequent and NOT simply resolved by the lower model index (which is
+    # what a visiting order that ignores the tree would do)
+    ids = want["primary_id"][want["primary_id"] != 0xFFFFFFFF]
+    twin = {}
+    for i in range(2 * n):
+        twin.setdefault(models["position"][i].tobytes() + models["radius"][i].tobytes(), []).append(i)
+    first_of_pair = {min(v) for v in twin.values()}
+    hit_first = np.isin(ids, list(first_of_pair)).mean()
+    assert len(ids) > 1000 and hit_first < 0.9
