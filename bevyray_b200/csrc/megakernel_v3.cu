@@ -425,10 +425,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 if (state == TRAVERSE) {
                     uint32_t c = cur;
                     if (Q16 ? c < Q16_LEAF : (S4 ? c < S4_LEAF : c < V3_NONE)) {  // inner node: test its children
-                        uint32_t r0, r1;
-                        float d0, d1;
-                        bool h0, h1;
-                        if (S4) {
+                        if constexpr (S4) {
                             // four children in shared memory: key = 21 bits of entry distance | 11 bits of ref
                             const uint32_t na = s_pairs + c * 112u;
                             float4 q0, q1, q2, q3, q4, q5, rr;
@@ -452,8 +449,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                                               ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.w)) : 0xffffffffu;
                             k0 = sort4_park(k0, k1, k2, k3, sp_addr, STACK_STRIDE);
                             c = k0 != 0xffffffffu ? (k0 & S4_REF_MASK) : NONE;
-                            r0 = r1 = 0u; d0 = d1 = 0.0f; h0 = h1 = false;
-                        } else if (W4) {
+                        } else if constexpr (W4) {
                             // four children: key = 11 bits of entry distance | 21 bits of ref, 0xffffffff = not entered
                             uint4 qa, qb, qc, qd;
                             const uint4* np = sv.nodes4_q + 4u * c;
@@ -470,14 +466,18 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                                               ? (((__float_as_uint(e) >> 20) << 21) | qd.w) : 0xffffffffu;
                             k0 = sort4_park(k0, k1, k2, k3, sp_addr, STACK_STRIDE);
                             c = k0 != 0xffffffffu ? (k0 & Q16_REF_MASK) : NONE;
-                            r0 = r1 = 0u; d0 = d1 = 0.0f; h0 = h1 = false;
-                        } else if (Q16) {
+                        } else {
+                          // two children
+                          uint32_t r0, r1;
+                          float d0, d1;
+                          bool h0, h1;
+                          if constexpr (Q16) {
                             uint4 qa, qb;
                             ldg256u(sv.pairs_q + 2u * c, qa, qb);
                             r0 = qa.w; r1 = qb.w;
                             h0 = box_cull_q16(qa.x, qa.y, qa.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, d0);
                             h1 = box_cull_q16(qb.x, qb.y, qb.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, d1);
-                        } else {
+                          } else {
                             float4 q0, q1, q2;
                             if (SMEM_SCENE) {
                                 const uint32_t na = s_pairs + c * 64u;
@@ -493,11 +493,10 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                             }
                             h0 = box_cull(inv, ainv, noi, closest.t, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, d0);
                             h1 = box_cull(inv, ainv, noi, closest.t, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, d1);
-                        }
-                        const bool first0 = d0 < d1;         // ties go to the second child (reference LIFO order)
-                        if (W4 || S4) {
-                        } else if (h0 && h1) {
-                            if (Q16) {
+                          }
+                          const bool first0 = d0 < d1;         // ties go to the second child (reference LIFO order)
+                          if (h0 && h1) {
+                            if constexpr (Q16) {
                                 // far child: 11 bits of distance, rounded towards zero (conservative at pop time)
                                 sts32(sp_addr, ((__float_as_uint(first0 ? d1 : d0) >> 20) << 21) | (first0 ? r1 : r0));
                             } else {
@@ -505,8 +504,9 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                             }
                             sp_addr += STACK_STRIDE;
                             c = first0 ? r0 : r1;
-                        } else {
+                          } else {
                             c = h0 ? r0 : (h1 ? r1 : NONE);
+                          }
                         }
                     }
                     if (Q16 ? (c & Q16_LEAF) != 0u : (S4 ? (c & S4_LEAF) != 0u : (int)c < 0)) {   // leaf: park it, or wait for the batch test
