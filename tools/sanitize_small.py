@@ -27,7 +27,7 @@ out = ctx.render(cam, 3, win, bvr.make_options(W))
 print("gpu-bvh", bvr.validate_bvh(nodes, scene.models), all(np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)) for k in ref))
 # megakernel variants chosen through the environment (tests/test_gpu_layouts.py)
 ctx.upload_scene(scene.models, scene.materials, scene.nodes)
-for env in ({"BVR_NO_BVH4": "1"}, {"BVR_MK_VARIANT": "4"}, {"BVR_MK_VARIANT": "2"}):
+for env in ({"BVR_NO_TIGHT": "1"}, {"BVR_NO_BVH4": "1"}, {"BVR_MK_VARIANT": "4"}, {"BVR_MK_VARIANT": "2"}):
     os.environ.update(env)
     out = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
     for k in env:
