@@ -60,6 +60,8 @@ struct BvrContext {
     DeviceBuffer raw_models, raw_materials, raw_nodes;
     DeviceBuffer spheres, sphere_material, pairs, pairs_ch, inner_id, block_sums, root_ref;
     DeviceBuffer model_rank;                  // position of every model in the reference's traversal order
+    DeviceBuffer validate_scratch, validate_out;   // GPU-side validation of big node arrays (scene_validate.cu)
+    ValidateOut* validate_host = nullptr;     // pinned
     DeviceBuffer nodes4_ch;                   // 4-wide fp32 records (scenes staged in shared memory)
     bool nodes4_ch_built = false;
     DeviceBuffer raw_nodes_tight, pairs_tight, pairs_ch_tight, nodes4_tight, tight_groups;   // tight-box variant
@@ -293,6 +295,8 @@ int bvr_create(int device, BvrContext** out_ctx) {
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->wf_host_counts, 8 * sizeof(unsigned int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->depth_host, sizeof(unsigned int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->q16_bad_host, sizeof(unsigned int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->validate_host, sizeof(ValidateOut), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = ctx->validate_out.ensure(sizeof(ValidateOut));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->q16_done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -312,13 +316,14 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->pairs_ch, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->validate_scratch, &ctx->validate_out, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
     if (ctx->ray_counter_host) cudaFreeHost(ctx->ray_counter_host);
     if (ctx->wf_host_counts) cudaFreeHost(ctx->wf_host_counts);
     if (ctx->q16_bad_host) cudaFreeHost(ctx->q16_bad_host);
+    if (ctx->validate_host) cudaFreeHost(ctx->validate_host);
     if (ctx->q16_done) cudaEventDestroy(ctx->q16_done);
     if (ctx->depth_host) cudaFreeHost(ctx->depth_host);
     cudaEvent_t evs[] = {ctx->ev_render0, ctx->ev_render1, ctx->ev_upload0, ctx->ev_upload1, ctx->upload_done};
@@ -364,10 +369,21 @@ int bvr_upload_scene(BvrContext* ctx,
     if (ranges && !ctx->scene_uploaded)
         return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "dirty ranges given before any full upload");
 
-    uint32_t depth = 0, n_inner = 0, max_leaf = 0;
+    // Small trees are validated on the host before anything is touched; big ones on the GPU, on the uploaded bytes
+    // (scene_validate.cu: the host walk costs 80 ms for 2 M nodes).  BVR_GPU_VALIDATE=0/1 forces either.
+    const int gv_env = env_int("BVR_GPU_VALIDATE", -1);
+    bool gpu_validate = n_nodes > 0 && (gv_env >= 0 ? gv_env != 0 : n_nodes >= 32768u);
+    uint32_t depth = ctx->tree_depth, n_inner = ctx->n_inner, max_leaf = ctx->max_leaf_models;
     std::vector<uint32_t> rank;
-    int st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth, &n_inner, &max_leaf, &rank);
-    if (st != BVR_OK) return st;
+    int st = BVR_OK;
+    if (!gpu_validate) {
+        st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth, &n_inner, &max_leaf, &rank);
+        if (st != BVR_OK) return st;
+    } else {
+        if (n_models > 0 && n_materials == 0) return fail(ctx, BVR_ERR_BAD_SCENE, "models without materials");
+        if (n_models >= (size_t)BVR_LEAF_FIRST_MASK) return fail(ctx, BVR_ERR_BAD_SCENE, "more than 2^24-1 models");
+        if (n_nodes >= 0x7fffffffull) return fail(ctx, BVR_ERR_BAD_SCENE, "too many BVH nodes");
+    }
 
     // the ranges to copy
     struct Copy { uint32_t array; size_t first, count; };
@@ -417,7 +433,33 @@ int bvr_upload_scene(BvrContext* ctx,
         if (c.array == BVR_ARRAY_MODELS) models_dirty = true;
         if (c.array == BVR_ARRAY_BVH_NODES) nodes_dirty = true;
     }
-    if ((nodes_dirty || !partial) && n_models) {
+    int launches = 0;
+    if (gpu_validate && (nodes_dirty || !partial)) {
+        BVR_CK(ctx->validate_scratch.ensure(validate_scratch_bytes((uint32_t)n_nodes)));
+        launches += launch_validate_scene(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, (uint32_t)n_models,
+                                          ctx->validate_scratch.ptr, ctx->model_rank.as<uint32_t>(),
+                                          ctx->validate_out.as<ValidateOut>(), ctx->stream);
+        BVR_CK(cudaMemcpyAsync(ctx->validate_host, ctx->validate_out.ptr, sizeof(ValidateOut), cudaMemcpyDeviceToHost, ctx->stream));
+        BVR_CK(cudaStreamSynchronize(ctx->stream));   // the verdict, the stack bound and the leaf size are needed now
+        const ValidateOut v = *ctx->validate_host;
+        if (v.bad) {
+            ctx->scene_uploaded = false;              // the previous scene's bytes are already overwritten
+            ctx->has_scene = false;
+            return fail(ctx, BVR_ERR_BAD_SCENE,
+                        (v.bad & BVR_VALIDATE_TWICE) ? "BVH node referenced twice (cycle or DAG)"
+                        : (v.bad & BVR_VALIDATE_CHILD_RANGE) ? "child index out of bounds"
+                        : (v.bad & BVR_VALIDATE_LEAF_RANGE) ? "leaf model range out of bounds"
+                                                            : "leaf with more than 128 models");
+        }
+        depth = v.depth; n_inner = v.n_inner; max_leaf = v.max_leaf;
+        if (depth > BVR_VALIDATE_MAX_DEPTH) {
+            // a degenerate, chain-like tree: the ranks come from the host walk after all
+            st = validate_scene(ctx, models, n_models, n_materials, nodes, n_nodes, &depth, &n_inner, &max_leaf, &rank);
+            if (st != BVR_OK) return st;
+            gpu_validate = false;
+        }
+    }
+    if (!gpu_validate && (nodes_dirty || !partial) && n_models) {
         // derived on the host from the node array (the walk above): 4 bytes per model travel with every new tree
         st = h2d(ctx, ctx->model_rank.ptr, rank.data(), n_models * sizeof(uint32_t), ctx->upload_staging, off);
         if (st != BVR_OK) return st;
@@ -426,7 +468,6 @@ int bvr_upload_scene(BvrContext* ctx,
     ctx->upload_pending = true;
 
     // derive the traversal layout in HBM
-    int launches = 0;
     if (models_dirty || !partial)
         launches += launch_derive_spheres(ctx->raw_models.as<RawModel>(), (uint32_t)n_models,
                                           ctx->spheres.as<float4>(), ctx->sphere_material.as<uint32_t>(), ctx->stream);

@@ -88,6 +88,17 @@ int launch_derive_nodes4_ch(const RawNode* nodes, uint32_t n_nodes, const uint32
 int launch_derive_tight(const RawNode* nodes, uint32_t n_nodes, const float4* spheres, uint32_t n_models, float pad,
                         float4* groups, RawNode* nodes_tight, cudaStream_t stream);
 
+// ---- structural validation of big node arrays on the GPU (scene_validate.cu) ----
+struct ValidateOut { uint32_t bad, depth, max_leaf, n_inner; };
+#define BVR_VALIDATE_LEAF_TOO_BIG 1u
+#define BVR_VALIDATE_LEAF_RANGE 2u
+#define BVR_VALIDATE_CHILD_RANGE 4u
+#define BVR_VALIDATE_TWICE 8u
+#define BVR_VALIDATE_MAX_DEPTH 2048u
+size_t validate_scratch_bytes(uint32_t n_nodes);
+int launch_validate_scene(const RawNode* nodes, uint32_t n_nodes, uint32_t n_models, void* scratch, uint32_t* model_rank,
+                          ValidateOut* out, cudaStream_t stream);
+
 // ---- GPU BVH builder (bvh_build.cu) ----
 size_t bvh_build_scratch_bytes(uint32_t n_models);
 int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, uint32_t* model_rank, void* scratch,

@@ -11,7 +11,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-KNOBS = ("BVR_NO_BVH4", "BVR_NO_Q16", "BVR_MK_VARIANT", "BVR_MK_V1", "BVR_MK_THREADS")
+KNOBS = ("BVR_NO_BVH4", "BVR_NO_Q16", "BVR_NO_TIGHT", "BVR_MK_VARIANT", "BVR_MK_V1", "BVR_MK_THREADS", "BVR_GPU_VALIDATE")
 
 
 def bits(a):
@@ -99,7 +99,8 @@ def test_quantised_records_refuse_boxes_outside_the_root(bvr, oracle, ctx, knobs
 
 
 @pytest.mark.parametrize("gpu_bvh", [False, True], ids=["host-ploc", "gpu-lbvh"])
-@pytest.mark.parametrize("env", [dict(), dict(BVR_NO_TIGHT=1), dict(BVR_NO_BVH4=1), dict(BVR_MK_VARIANT=4), dict(BVR_MK_V1=1)],
+@pytest.mark.parametrize("env", [dict(), dict(BVR_NO_TIGHT=1), dict(BVR_NO_BVH4=1), dict(BVR_MK_VARIANT=4), dict(BVR_MK_V1=1),
+                                 dict(BVR_GPU_VALIDATE=1)],
                          ids=lambda e: "-".join(f"{k[4:]}={v}" for k, v in e.items()) or "default")
 def test_exact_ties_go_to_the_sphere_the_reference_reaches_first(bvr, oracle, ctx, knobs, env, gpu_bvh):
     """Two spheres with bit-identical t: the reference keeps the one it visits first (strict <, raytrace.wgsl:354),
@@ -142,3 +143,37 @@ def test_exact_ties_go_to_the_sphere_the_reference_reaches_first(bvr, oracle, ct
     first_of_pair = {min(v) for v in twin.values()}
     hit_first = np.isin(ids, list(first_of_pair)).mean()
     assert len(ids) > 1000 and hit_first < 0.9
+
+
+def test_gpu_side_validation_rejects_what_the_host_walk_rejects(bvr, rtiow, knobs):
+    """Node arrays of 32 k entries and more are validated on the GPU (scene_validate.cu); forced here on the small
+    scene so that the same malformed trees go through both implementations."""
+    cp = bvr.capi
+    for gv in (0, 1):
+        knobs(BVR_GPU_VALIDATE=gv)
+        c = bvr.Context(0)
+        cases = []
+        bad = rtiow.nodes.copy(); bad["index"][0] = 0; cases.append(bad)                     # root points at itself
+        bad = rtiow.nodes.copy()
+        leaf = int(np.nonzero(bad["model_count"] > 0)[0][0])
+        bad["index"][leaf] = len(rtiow.models); cases.append(bad)                              # leaf beyond the models
+        bad = rtiow.nodes.copy()
+        inner = np.nonzero(bad["model_count"] == 0)[0]
+        bad["index"][inner[3]] = len(bad) - 1; cases.append(bad)                               # second child out of range
+        bad = rtiow.nodes.copy(); bad["index"][inner[5]] = bad["index"][inner[7]]; cases.append(bad)   # two parents
+        bad = rtiow.nodes.copy(); bad["model_count"][leaf] = 200; cases.append(bad)           # leaf too large
+        for k, nodes in enumerate(cases):
+            with pytest.raises(bvr.BvrError) as e:
+                c.upload_scene(rtiow.models, rtiow.materials, nodes)
+            assert e.value.status == cp.BVR_ERR_BAD_SCENE, (gv, k)
+        # the context stays usable after errors
+        c.upload_scene(rtiow.models, rtiow.materials, rtiow.nodes)
+        W, H = 64, 36
+        cam = bvr.make_camera(sample_count=1, bounces=3, aspect=W / H)
+        out = c.render(cam, 3, bvr.make_window(0.2, H), bvr.make_options(W))
+        st = c.stats()
+        c.close()
+        if gv == 0:
+            ref, ref_rays = out, st["rays"]
+        else:
+            assert st["rays"] == ref_rays and all(np.array_equal(bits(out[k]), bits(ref[k])) for k in ref)

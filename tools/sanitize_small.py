@@ -44,4 +44,10 @@ for env in ({}, {"BVR_NO_BVH4": "1"}, {"BVR_NO_Q16": "1"}):
         del os.environ[k]
     bref = bref or out
     print("big", env, all(np.array_equal(out[k].view(np.uint32), bref[k].view(np.uint32)) for k in bref))
+# structural validation on the GPU (scene_validate.cu), forced on the small scene
+os.environ["BVR_GPU_VALIDATE"] = "1"
+ctx.upload_scene(scene.models, scene.materials, scene.nodes)
+out = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
+del os.environ["BVR_GPU_VALIDATE"]
+print("gpu-validate", all(np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)) for k in ref))
 print("done")
