@@ -79,6 +79,7 @@ struct BvrContext {
     uint32_t max_leaf_models = 0;
     int sm_count = 0;
     DeviceBuffer pixel_counter;
+    DeviceBuffer px_acc;                      // per-pixel accumulators of the v5 experiment
     DeviceBuffer wf_state;
     DeviceBuffer bvh_scratch;
     unsigned int* depth_host = nullptr;       // pinned
@@ -316,7 +317,7 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->pairs_ch, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->validate_scratch, &ctx->validate_out, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->px_acc, &ctx->validate_scratch, &ctx->validate_out, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
@@ -746,6 +747,15 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
                                              ctx->sm_count, ctx->stream);
                     if (forced) break;
                 }
+                if (n < 0) cudaGetLastError();
+            }
+            if (variant == 5) {
+                BVR_CK(ctx->px_acc.ensure((size_t)p.cam.width * p.shard.rows * sizeof(float4)));
+                n = launch_megakernel_v5(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
+                                         ctx->pixel_counter.as<unsigned int>(), ctx->px_acc.as<float4>(),
+                                         (uint32_t)env_int("BVR_MK5_SHADERS", 8), (uint32_t)env_int("BVR_MK5_SWAP", 8),
+                                         (uint32_t)env_int("BVR_MK5_EXTRA", 192), (uint32_t)env_int("BVR_MK5_BATCH", 24),
+                                         ctx->sm_count, ctx->stream);
                 if (n < 0) cudaGetLastError();
             }
             const int candidates[4] = {1024, 768, 512, 256};

@@ -119,6 +119,11 @@ int launch_megakernel_v4(const RenderParams& p, uint32_t n_inner, uint32_t n_mod
                          uint32_t max_leaf_models, unsigned int* pixel_counter, int threads, uint32_t shade_lanes,
                          uint32_t stuck_lanes, uint32_t switch_lanes, uint32_t leaf_batch_lanes, int sm_count,
                          cudaStream_t stream);
+// warp-specialised kernel with a per-CTA ray pool (v5, experiment); -1 when the scene does not qualify -> use v3.
+// px_acc: one float4 per shard pixel (accumulators live in HBM/L2)
+int launch_megakernel_v5(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
+                         unsigned int* pixel_counter, float4* px_acc, uint32_t shader_warps, uint32_t swap_lanes,
+                         uint32_t extra_paths, uint32_t min_batch, int sm_count, cudaStream_t stream);
 size_t wavefront_state_bytes(size_t slots);
 void wavefront_bind(WavefrontParams& w, void* state, size_t slots);
 // persistent per-CTA wavefront (cta_wavefront.cu): number of path slots it needs, and the launch
