@@ -109,6 +109,7 @@ SIGNATURES = {
     "bvr_upload_scene": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
     "bvr_upload_scene_gpu_bvh": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
     "bvr_shard_rows": (_u32, [_u32, _P(BvrRenderOptions)]),
+    "bvr_scene_traversal_ranks": (_i, [_vp, _sz, _sz, _vp, _vp]),
     "bvr_render": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _P(BvrWindow), _P(BvrRenderOptions), _vp, _vp, _P(BvrOutputs)]),
     "bvr_render_device": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _P(BvrWindow), _P(BvrRenderOptions), _vp, _vp, _P(BvrOutputs)]),
     "bvr_axpby_device": (_i, [_vp, _vp, _f, _vp, _f, _sz]),

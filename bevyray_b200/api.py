@@ -126,6 +126,18 @@ def validate_bvh(nodes, models):
     return None if rc == 0 else msg.value.decode()
 
 
+def traversal_ranks(nodes, n_models):
+    """Position of every model in the reference's traversal order + the number of tree levels
+    (bvr_scene_traversal_ranks: host only, what bvr_upload_scene derives for the tie rule)."""
+    nodes = np.ascontiguousarray(nodes, dtype=BVH_NODE_DTYPE)
+    ranks = np.empty(n_models, np.uint32)
+    depth = C.c_uint32()
+    st = lib.bvr_scene_traversal_ranks(_ptr(nodes), len(nodes), n_models, _ptr(ranks), C.byref(depth))
+    if st != capi.BVR_OK:
+        raise BvrError(st, "bvr_scene_traversal_ranks")
+    return ranks, depth.value
+
+
 class Context:
     """One GPU context (bvr_create / bvr_destroy)."""
 

@@ -604,6 +604,18 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
 
 uint32_t bvr_shard_rows(uint32_t height, const BvrRenderOptions* opts) { return shard_rows_impl(height, opts); }
 
+int bvr_scene_traversal_ranks(const BvrBvhNode* nodes, size_t n_nodes, size_t n_models, uint32_t* out_ranks,
+                              uint32_t* out_depth) {
+    if (n_nodes && !nodes) return BVR_ERR_INVALID_ARGUMENT;
+    uint32_t depth = 0, n_inner = 0, max_leaf = 0;
+    std::vector<uint32_t> rank;
+    const int st = validate_scene(nullptr, nullptr, n_models, n_models ? 1 : 0, nodes, n_nodes, &depth, &n_inner, &max_leaf, &rank);
+    if (st != BVR_OK) return st;
+    if (out_ranks) std::memcpy(out_ranks, rank.data(), n_models * sizeof(uint32_t));
+    if (out_depth) *out_depth = depth;
+    return BVR_OK;
+}
+
 static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level,
                         const BvrWindow* window, const BvrRenderOptions* opts, RenderParams* out) {
     if (!camera || !level || !window || !opts) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null uniform / options pointer");

@@ -231,6 +231,16 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
 /* Rows this shard renders for an image of `height` rows (== height when unsharded). */
 uint32_t bvr_shard_rows(uint32_t height, const BvrRenderOptions* opts);
 
+/* Host-only helper (no context, no GPU): validates a node array against the reference's contract the way
+ * bvr_upload_scene does and reports what the upload derives from it — the number of tree levels and, per model, its
+ * position in the reference's traversal order (raytrace.wgsl:329-341 pops `index + 1` before `index`, so the order
+ * over the leaves is fixed by the tree).  raytrace.wgsl:354 keeps the FIRST sphere that reaches a given t; the
+ * kernels, which visit nodes in another order, resolve bit-exact ties in t towards the lower rank.
+ * out_ranks: n_models words (0xFFFFFFFF for a model no reachable leaf holds), may be NULL; out_depth may be NULL.
+ * Returns BVR_OK or BVR_ERR_BAD_SCENE / BVR_ERR_INVALID_ARGUMENT. */
+int bvr_scene_traversal_ranks(const BvrBvhNode* nodes, size_t n_nodes, size_t n_models,
+                              uint32_t* out_ranks, uint32_t* out_depth);
+
 /* Render one frame for one view with HOST buffers: inputs are copied host->device, outputs
  * device->host, and the call returns when the outputs are complete.
  * raster_rgba: 4 floats / pixel (the post-tonemap main texture, pipeline.rs:166), full image;

@@ -143,3 +143,42 @@ def test_random_scene_and_animation(bvr):
     assert bvr.validate_bvh(s.nodes, s.models) is None
     s.animate(0)
     assert np.allclose(s.models["position"][1], base["position"][1])
+
+
+def _reference_leaf_order(nodes):
+    """The order in which raytrace.wgsl:313-346 reaches the leaves when nothing is culled: the stack starts with
+    node 0; an inner node pushes `index` and then `index + 1`, so `index + 1` is popped first."""
+    order, stack = [], [0]
+    while stack:
+        i = stack.pop()
+        if nodes["model_count"][i] > 0:
+            order.extend(range(int(nodes["index"][i]), int(nodes["index"][i]) + int(nodes["model_count"][i])))
+        else:
+            stack.append(int(nodes["index"][i]))
+            stack.append(int(nodes["index"][i]) + 1)
+    return order
+
+
+def test_traversal_ranks_follow_the_reference_order(bvr):
+    """bvr_scene_traversal_ranks (host only): every model's position in the reference's traversal order, which
+    the kernels use to resolve bit-exact ties in t the way the reference's strict `<` does."""
+    for scene in (bvr.Scene.rtiow(1), bvr.Scene.random(3, 777, 20.0, 0.05, 0.4)):
+        ranks, depth = bvr.traversal_ranks(scene.nodes, len(scene.models))
+        order = _reference_leaf_order(scene.nodes)
+        assert sorted(order) == list(range(len(scene.models)))
+        want = np.empty(len(order), np.uint32)
+        want[order] = np.arange(len(order), dtype=np.uint32)
+        assert np.array_equal(ranks, want)
+        assert 1 < depth < 64
+    # multi-model leaves keep buffer order inside the leaf; models no leaf holds get 0xFFFFFFFF
+    nodes = np.zeros(3, bvr.BVH_NODE_DTYPE)
+    nodes["index"][0], nodes["model_count"][0] = 1, 0
+    nodes["index"][1], nodes["model_count"][1] = 0, 3
+    nodes["index"][2], nodes["model_count"][2] = 4, 2
+    ranks, depth = bvr.traversal_ranks(nodes, 7)
+    assert list(ranks) == [2, 3, 4, 0xFFFFFFFF, 0, 1, 0xFFFFFFFF] and depth == 2
+    # a cycle is rejected like at upload time
+    nodes["index"][0] = 0
+    with pytest.raises(bvr.BvrError) as e:
+        bvr.traversal_ranks(nodes, 7)
+    assert e.value.status == bvr.capi.BVR_ERR_BAD_SCENE
