@@ -218,17 +218,41 @@ __global__ void __launch_bounds__(THREADS) megakernel_v5(const RenderParams p, u
 
     uint32_t rays = 0;
 
-    if (warp < tune.shader_warps) {
-        // ============================== shader warp ==============================
-        for (;;) {
-            if (warp_read(v_finished, lane)) break;
+    // the ray a traversal lane holds, and the rest of its path (which travels with the ray)
+    const bool dedicated_shader = warp < tune.shader_warps;
+    int state = L5_IDLE;
+    Ray ray{v3(0, 0, 0), v3(0, 0, 1)};
+    V3 inv = v3(0, 0, 0), ainv = v3(0, 0, 0), noi = v3(0, 0, 0);
+    float a = 1.0f;
+    Hit closest{BVR_INF, 0xffffffffu};
+    uint32_t cur = V5_NONE, pending = V5_NONE;
+    uint32_t sp_addr = s_stack0;
+    bool far_ray = false;
+    float4 g2 = make_float4(1.f, 1.f, 1.f, 0.f);   // throughput, rng
+    float4 g3 = make_float4(0.f, 0.f, 0.f, 0.f);   // pixel, sample|bounce, first depth, -
+    uint32_t cooldown = 0;   // vote rounds to traverse before the next exchange attempt (after a fruitless one)
+    uint32_t backoff = 64;   // ns to sleep when there is nothing to do (doubles up to 2 us)
+
+    for (;;) {
+        // ---- what does this warp do now?  Dedicated shader warps always shade; a traversal warp that holds no ray
+        //      shades too when a whole batch waits or when there is nothing to traverse (a warp that only polls
+        //      steals issue slots from the shaders it is waiting for: ncu on the first version) ----
+        const unsigned m_fin = __ballot_sync(full, state == L5_FINISHED);
+        const unsigned m_idle = __ballot_sync(full, state == L5_IDLE);
+        const unsigned m_trav = __ballot_sync(full, state == L5_TRAVERSE);
+        const bool empty = (m_trav | m_fin) == 0u;
+        if (empty && warp_read(v_finished, lane)) break;
+        const unsigned int waiting = warp_read(v_shade, lane);
+        const unsigned int ready_now = warp_read(v_ready, lane);
+        const bool shade_now = empty && (dedicated_shader || waiting >= 32u || (waiting > 0u && ready_now == 0u));
+        if (shade_now) {
+            // ============================== shading pass ==============================
             uint32_t eid = 0;
-            // wait for a decent batch unless the traversal side is running out of rays
-            const unsigned int waiting = warp_read(v_shade, lane);
-            const unsigned int ready_now = warp_read(v_ready, lane);
             const unsigned int nomore = warp_read(v_nomore, lane);
             uint32_t n = 0;
-            if (waiting >= tune.min_batch || (waiting > 0u && ready_now < 64u)) n = ring_pop(&ctl->shade_q, ring_shade, 32u, eid, lane);
+            // dedicated warps wait for a decent batch unless the traversal side is running out of rays
+            if (!dedicated_shader || waiting >= tune.min_batch || (waiting > 0u && ready_now < 64u))
+                n = ring_pop(&ctl->shade_q, ring_shade, 32u, eid, lane);
             // spawn new paths while the population is below target and pixels remain
             uint32_t m = 0;
             if (n < 32u && !nomore) {
@@ -247,9 +271,11 @@ __global__ void __launch_bounds__(THREADS) megakernel_v5(const RenderParams p, u
             }
             if (n + m == 0u) {
                 if (lane == 0u && *v_nomore && *v_live == 0u) *v_finished = 1u;
-                __nanosleep(100);
+                __nanosleep(backoff);
+                if (backoff < 2048u) backoff *= 2u;
                 continue;
             }
+            backoff = 64;
             const bool mine = lane < n + m;
             const uint32_t eb = s_pool + eid * 16u;
             int ps = !mine ? P5_NONE : (lane < n ? P5_SHADE : P5_EMPTY);
@@ -436,28 +462,16 @@ __global__ void __launch_bounds__(THREADS) megakernel_v5(const RenderParams p, u
                 ring_push(&ctl->free_q, ring_free, ps == P5_DEAD, eid, lane);
                 if (lane == 0u) { atomicSub(&ctl->live_paths, (unsigned)__popc(dead)); *v_nomore = 1u; }
             }
+            continue;
         }
-    } else {
-        // ============================== traversal warp ==============================
-        int state = L5_IDLE;
-        Ray ray{v3(0, 0, 0), v3(0, 0, 1)};
-        V3 inv = v3(0, 0, 0), ainv = v3(0, 0, 0), noi = v3(0, 0, 0);
-        float a = 1.0f;
-        Hit closest{BVR_INF, 0xffffffffu};
-        uint32_t cur = V5_NONE, pending = V5_NONE;
-        uint32_t sp_addr = s_stack0;
-        bool far_ray = false;
-        // the rest of the path travels with the ray
-        float4 g2 = make_float4(1.f, 1.f, 1.f, 0.f);   // throughput, rng
-        float4 g3 = make_float4(0.f, 0.f, 0.f, 0.f);   // pixel, sample|bounce, first depth, -
-        uint32_t cooldown = 0;   // vote rounds to traverse before the next exchange attempt (after a fruitless one)
-
-        for (;;) {
+        if (dedicated_shader) {            // nothing to shade yet
+            __nanosleep(backoff);
+            if (backoff < 2048u) backoff *= 2u;
+            continue;
+        }
+        {
+            // ============================== traversal ==============================
             // ---- exchange: finished lanes swap against ready rays; idle lanes pull; leftovers deposit ----
-            const unsigned m_fin = __ballot_sync(full, state == L5_FINISHED);
-            const unsigned m_idle = __ballot_sync(full, state == L5_IDLE);
-            const unsigned m_trav = __ballot_sync(full, state == L5_TRAVERSE);
-            if (m_trav == 0u && m_fin == 0u && warp_read(v_finished, lane)) break;
             const uint32_t n_need = (uint32_t)__popc(m_fin | m_idle);
             uint32_t rid = 0;
             uint32_t got = ring_pop(&ctl->ready_q, ring_ready, n_need, rid, lane);
@@ -527,7 +541,12 @@ __global__ void __launch_bounds__(THREADS) megakernel_v5(const RenderParams p, u
             ring_push(&ctl->free_q, ring_free, push_free, push_free_id, lane);
 
             const unsigned trav_now = __ballot_sync(full, state == L5_TRAVERSE);
-            if (trav_now == 0u) { __nanosleep(100); continue; }
+            if (trav_now == 0u) {
+                __nanosleep(backoff);
+                if (backoff < 2048u) backoff *= 2u;
+                continue;
+            }
+            backoff = 64;
             // nothing moved although lanes wanted to: the pool had no ray / no room for them; do not come back at once
             cooldown = (__ballot_sync(full, gets || deposits) == 0u && n_need > 0u) ? 4u : 0u;
 
