@@ -473,10 +473,14 @@ def main():
     ap.add_argument("--reference-order", action="store_true", help="reference traversal order (raytrace.wgsl:313-346)")
     ap.add_argument("--shard", default="samples", choices=["samples", "tiles"])
     ap.add_argument("--strip-rows", type=int, default=4)
-    ap.add_argument("--cpu-spp", type=int, default=4, help="samples per pixel of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-spp", type=int, default=0,
+                    help="samples per pixel of the bounded CPU-baseline sample (0 = per workload: about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--spp", type=int, default=0, help="PROFILING ONLY: override samples per pixel (the line is then not a bench value)")
     args = ap.parse_args()
+    if args.cpu_spp <= 0:
+        # ~17 Mrays/s (C2/C3) and ~1 Mrays/s (C4) on 16 host cores: 32 spp of C2 = 165 M rays ~ 10 s, 4 spp of C4 ~ 25 s
+        args.cpu_spp = {"c1": 1, "c2": 32, "c3": 8, "c4": 4}.get(args.workload, 4)
     if args.spp:
         for wl in WORKLOADS.values():
             wl["spp"] = args.spp
