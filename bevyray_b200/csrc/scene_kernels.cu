@@ -130,6 +130,7 @@ __global__ void build_pairs_kernel(const RawNode* __restrict__ nodes, uint32_t n
 // Quantisation grid of the 32-byte records: 65536 steps per axis across the root box plus two steps of margin on
 // either side (so that the outward rounding below never has to clamp inside the root box).
 struct QGrid { float base[3], step[3]; };
+#define BVR_Q16_MAX_STEP 0.005f   // two steps = a tenth of the reference's 0.1 pad
 
 __device__ __forceinline__ QGrid make_qgrid(const RawNode& root) {
     QGrid g;
@@ -156,6 +157,11 @@ __global__ void build_pairs_q16_kernel(const RawNode* __restrict__ nodes, uint32
 #pragma unroll
         for (int k = 0; k < 3; k++) { grid_out[k] = g.base[k]; grid_out[4 + k] = g.step[k]; }
         grid_out[3] = 0.0f; grid_out[7] = 0.0f;
+        // Outward rounding moves a box face by up to two grid steps.  That must stay small against the reference's
+        // own pad of 0.1 (extract.rs:223-224): where the pad is all that separates "ray enters the box" from "f32
+        // noise in hit_sphere", a visibly larger box finds hits the reference culls (tools/big_fuzz.py case 11:
+        // extent 3400, step 0.05 -> 5 of 44150 rays differ).  Scenes wider than ~330 units keep the fp32 records.
+        if (g.step[0] > BVR_Q16_MAX_STEP || g.step[1] > BVR_Q16_MAX_STEP || g.step[2] > BVR_Q16_MAX_STEP) *bad = 1u;
     }
     const RawNode nd = nodes[i];
     if (nd.model_count != 0u) {

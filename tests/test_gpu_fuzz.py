@@ -50,3 +50,53 @@ def test_random_scene_scales(bvr, oracle, ctx, it):
     for k in ("primary_id", "primary_depth", "rt_depth", "rgba"):
         assert np.array_equal(np.ascontiguousarray(got[k]).view(np.uint32), np.ascontiguousarray(want[k]).view(np.uint32)), k
     assert rays == cnt["rays"]
+
+
+def make_big_case(bvr, it):
+    """tools/big_fuzz.py's generator: 2 k - 120 k spheres at C4's density, uniform or clustered, four decades of scale."""
+    rs = np.random.RandomState(500 + it)
+    n = int(rs.choice([2000, 6000, 20000, 50000, 120000]))
+    scale = float(10.0 ** rs.uniform(-2, 2))
+    side = float((n / 0.125) ** (1 / 3.0))
+    models = np.zeros(n, bvr.MODEL_DTYPE)
+    if rs.rand() < 0.5:
+        pos = rs.uniform(-0.5, 0.5, (n, 3)) * side
+    else:
+        centres = rs.uniform(-0.5, 0.5, (8, 3)) * side
+        pos = centres[rs.randint(0, 8, n)] + rs.normal(size=(n, 3)) * side * 0.04
+    models["position"] = (pos * scale).astype(np.float32)
+    models["radius"] = (rs.uniform(0.05, 0.25, n) * scale).astype(np.float32)
+    models["material_id"] = rs.randint(0, 4, n)
+    mats = np.zeros(4, bvr.MATERIAL_DTYPE)
+    mats["base_color"] = rs.uniform(0.2, 0.95, (4, 3)).astype(np.float32)
+    mats["metallic"] = [0.0, 1.0, 0.0, 0.4]
+    mats["roughness"] = [0.5, 0.1, 0.0, 0.6]
+    mats["ior"] = 1.5
+    mats["specular_transmission"] = [0.0, 0.0, 1.0, 0.3]
+    gpu_bvh = bool(rs.rand() < 0.4)
+    d = rs.normal(size=3)
+    d /= np.linalg.norm(d)
+    dist = side * scale * float(rs.uniform(0.2, 1.5))
+    cam = bvr.make_camera(position=tuple(d * dist), target=(0, 0, 0), fov=float(rs.uniform(0.3, 1.0)), aspect=160 / 90,
+                          near=0.1 * scale, far=1e5 * scale, sample_count=2, bounces=8)
+    return models, mats, cam, float(rs.rand()), gpu_bvh
+
+
+@pytest.mark.parametrize("it", [0, 2, 3, 5, 6, 11, 13, 16])
+def test_random_big_scenes(bvr, oracle, ctx, it):
+    """Scenes walked in HBM/L2.  Case 11 (extent 3400 units, spheres of radius 2-10, the reference's pad of 0.1 far
+    below the f32 noise of hit_sphere there) is the one that made the 16-bit grid conditional on its step size."""
+    models, mats, cam, seed, gpu_bvh = make_big_case(bvr, it)
+    if gpu_bvh:
+        nodes = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
+    else:
+        nodes = bvr.build_ploc(models)
+        ctx.upload_scene(models, mats, nodes)
+    win = bvr.make_window(seed, 90)
+    got = ctx.render(cam, 3, win, bvr.make_options(160, kernel=1))
+    rays = ctx.stats()["rays"]
+    want, cnt = oracle.render(models, mats, nodes, cam, bvr.make_level(3), win, 160)
+    assert cnt["stack_truncations"] == 0
+    for k in ("primary_id", "primary_depth", "rt_depth", "rgba"):
+        assert np.array_equal(np.ascontiguousarray(got[k]).view(np.uint32), np.ascontiguousarray(want[k]).view(np.uint32)), k
+    assert rays == cnt["rays"]
