@@ -773,15 +773,10 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
             const int candidates[4] = {1024, 768, 512, 256};
             for (int ci = 0; ci < 4 && n < 0; ci++) {
                 const int threads = (forced && variant != 4) ? forced : candidates[ci];
-                if (variant != 2)
-                    n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
-                                             ctx->pixel_counter.as<unsigned int>(), threads,
-                                             (uint32_t)env_int("BVR_MK_WAIT", 0), (uint32_t)env_int("BVR_MK_LEAF", 0),   // 0 = per-mode default
-                                             ctx->sm_count, ctx->stream);
-                else
-                    n = launch_megakernel_persistent(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
-                                                     ctx->pixel_counter.as<unsigned int>(), threads,
-                                                     (uint32_t)env_int("BVR_MK_WAIT", 28), ctx->sm_count, ctx->stream);
+                n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
+                                         ctx->pixel_counter.as<unsigned int>(), threads,
+                                         (uint32_t)env_int("BVR_MK_WAIT", 0), (uint32_t)env_int("BVR_MK_LEAF", 0),   // 0 = per-mode default
+                                         ctx->sm_count, ctx->stream);
                 if (forced && variant != 4) break;
             }
             if (n < 0) cudaGetLastError();

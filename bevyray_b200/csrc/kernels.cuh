@@ -106,11 +106,8 @@ int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, uin
 
 // ---- render kernels ----
 int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple one-thread-per-pixel kernel (v1)
-// persistent-lane megakernel; returns -1 when the configuration does not fit (caller falls back to v1)
-int launch_megakernel_persistent(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
-                                 unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, int sm_count,
-                                 cudaStream_t stream);
-// staged-shading persistent megakernel (v3); same contract as launch_megakernel_persistent
+// staged-shading persistent-lane megakernel (v3); returns -1 when the configuration does not fit (the caller
+// falls back to v1)
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
                          int sm_count, cudaStream_t stream);

@@ -1,8 +1,8 @@
 // megakernel_v3.cu — persistent-lane megakernel with STAGED shading and postponed leaf tests.
 //
-// Same lane/pixel ownership, pixel queue and shared-memory staging as megakernel_persistent.cu (v2);
-// what changes is how divergent work is regrouped inside the warp (ncu on v2: 10 of 32 lanes active per
-// instruction, shading and sphere tests running at 4-5 lanes — profiles/r01_v2_*):
+// Persistent lanes: every lane owns one pixel at a time, taken from a tile-ordered queue; scene and traversal stacks
+// in shared memory.  How divergent work is regrouped inside the warp (ncu on the unstaged predecessor v2: 10 of 32
+// lanes active per instruction, shading and sphere tests running at 4-5 lanes — profiles/r01_v2_*):
 //
 //   * phase A is cut into stages that every waiting lane walks through together, each stage having ONE
 //     code site per expensive operation: classification draws (raytrace.wgsl:234,248) -> one shared

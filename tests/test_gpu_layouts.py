@@ -1,7 +1,7 @@
 """Every node layout / kernel variant of the megakernel against the oracle (bit-exact).  The variants are picked by
 the library from the scene; the environment knobs below force the others for A/B runs:
   small scenes (staged in shared memory): 4-wide fp32 records (default), child-pair records (BVR_NO_BVH4),
-      two paths per lane (BVR_MK_VARIANT=4), warp-specialised ray pool (BVR_MK_VARIANT=5), unstaged v2 (BVR_MK_VARIANT=2), one thread per pixel (BVR_MK_V1);
+      two paths per lane (BVR_MK_VARIANT=4), warp-specialised ray pool (BVR_MK_VARIANT=5), one thread per pixel (BVR_MK_V1);
   big scenes (walked in HBM/L2): 4-wide 16-bit records (default), 2-wide 16-bit records (BVR_NO_BVH4),
       fp32 child-pair records (BVR_NO_Q16, chosen at upload)."""
 import os
@@ -39,7 +39,7 @@ def check(got, want, cnt, stats, tag):
     assert stats["rays"] == cnt["rays"], tag
 
 
-SMALL = [dict(), dict(BVR_NO_BVH4=1), dict(BVR_MK_VARIANT=4), dict(BVR_MK_VARIANT=5), dict(BVR_MK_VARIANT=2), dict(BVR_MK_V1=1),
+SMALL = [dict(), dict(BVR_NO_BVH4=1), dict(BVR_MK_VARIANT=4), dict(BVR_MK_VARIANT=5), dict(BVR_MK_V1=1),
          dict(BVR_MK_THREADS=512), dict(BVR_NO_BVH4=1, BVR_MK_THREADS=768)]
 
 

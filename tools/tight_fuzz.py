@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Randomised parity sweep for the small-scene production layout (4-wide records, tight boxes, tie rule) against the
-oracle: scenes at very different scales, radius ratios and camera distances.  usage (GPU box): python tools/tight_fuzz.py [n]"""
+oracle: scenes at very different scales, radius ratios and camera distances.  usage (GPU box): python tools/tight_fuzz.py [n]
+FUZZ_SIZES=1025,1500,2500,4000 sweeps the sizes just above the 4-wide shared-memory layout (child-pair records in shared
+memory, then fp32 records in HBM/L2)."""
 import os
 import sys
 
@@ -16,7 +18,8 @@ ctx = bvr.Context(0)
 bad_total = 0
 for it in range(N):
     rs = np.random.RandomState(1000 + it)
-    n = int(rs.choice([2, 7, 40, 200, 600, 1024]))
+    sizes = [int(x) for x in os.environ.get("FUZZ_SIZES", "2,7,40,200,600,1024").split(",")]
+    n = int(rs.choice(sizes))
     scale = float(10.0 ** rs.uniform(-2, 2))                  # world units per scene unit
     spread = float(rs.choice([2.0, 8.0, 30.0]))
     models = np.zeros(n, bvr.MODEL_DTYPE)
@@ -41,7 +44,7 @@ for it in range(N):
                           near=0.1 * scale, far=1000.0 * scale * 50, sample_count=4, bounces=8)
     win = bvr.make_window(float(rs.rand()), H)
     ctx.upload_scene(models, mats, nodes)
-    got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
+    got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=int(os.environ.get("FUZZ_KERNEL", "1")), traversal=int(os.environ.get("FUZZ_TRAVERSAL", "0"))))
     rays = ctx.stats()["rays"]
     want, cnt = oracle.render(models, mats, nodes, cam, bvr.make_level(3), win, W)
     bad = sum(int((np.ascontiguousarray(got[k]).view(np.uint32) != np.ascontiguousarray(want[k]).view(np.uint32)).sum()) for k in want)
