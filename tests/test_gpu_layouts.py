@@ -177,3 +177,32 @@ def test_gpu_side_validation_rejects_what_the_host_walk_rejects(bvr, rtiow, knob
             ref, ref_rays = out, st["rays"]
         else:
             assert st["rays"] == ref_rays and all(np.array_equal(bits(out[k]), bits(ref[k])) for k in ref)
+
+
+def test_dirty_range_upload_of_a_big_scene(bvr, oracle, knobs):
+    """40 k spheres (80 k nodes: validated on the GPU), a few hundred of them moved, the tree rebuilt on the host and
+    only the dirty ranges uploaded: same image as the oracle's on the new scene, far fewer bytes than a full upload."""
+    knobs()
+    scene = bvr.Scene.random(9, 40000, 68.0, 0.05, 0.25)
+    models, mats = scene.models.copy(), scene.materials.copy()
+    W, H = 160, 90
+    cam = bvr.make_camera(position=(0, 0, 46), target=(0, 0, 0), aspect=W / H, sample_count=2, bounces=6)
+    win = bvr.make_window(0.44, H)
+    c = bvr.Context(0)
+    c.upload_scene(models, mats, scene.nodes)
+    c.render(cam, 3, win, bvr.make_options(W))
+    h2d0 = c.stats()["h2d_bytes"]
+    rs = np.random.RandomState(1)
+    moved = np.sort(rs.choice(len(models), 300, replace=False))
+    models["position"][moved] += rs.uniform(-0.2, 0.2, (300, 3)).astype(np.float32)
+    nodes = bvr.build_ploc(models)
+    changed = np.nonzero((nodes.view(np.uint8).reshape(-1, 48) != scene.nodes.view(np.uint8).reshape(-1, 48)).any(axis=1))[0]
+    ranges = [(bvr.capi.ARRAY_MODELS, int(i), 1) for i in moved]
+    ranges.append((bvr.capi.ARRAY_BVH_NODES, int(changed.min()), int(changed.max() - changed.min() + 1)))
+    c.upload_scene(models, mats, nodes, ranges)
+    got = c.render(cam, 3, win, bvr.make_options(W))
+    sent = c.stats()["h2d_bytes"] - h2d0
+    assert sent == 300 * 32 + int(changed.max() - changed.min() + 1) * 48     # ranks come from the GPU-side validation
+    want, cnt = oracle.render(models, mats, nodes, cam, bvr.make_level(3), win, W)
+    check(got, want, cnt, c.stats(), "dirty big scene")
+    c.close()
