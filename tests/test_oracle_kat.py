@@ -221,3 +221,34 @@ def test_store_srgb8(oracle):
     x = np.array([[0.0, 0.0031308, 0.5, 1.0], [2.0, -1.0, 0.2, 0.5]], np.float32)
     out = oracle.store_srgb8(x)
     assert out.tolist() == [[0, 10, 188, 255], [255, 0, 124, 128]]
+
+
+def test_exact_ties_go_to_the_leaf_popped_first(bvr, oracle):
+    """raytrace.wgsl:354 accepts a hit only if it is strictly nearer, and raytrace.wgsl:329-341 pops child `index + 1`
+    before child `index`: of two identical spheres in sibling leaves the reference reports the one in the SECOND leaf.
+    (The kernels reproduce this through the model ranks, bvr_scene_traversal_ranks.)"""
+    models = np.zeros(2, bvr.MODEL_DTYPE)
+    models["position"][:] = (0.0, 0.0, -5.0)
+    models["radius"][:] = 1.0
+    models["material_id"] = [0, 1]
+    mats = np.zeros(2, bvr.MATERIAL_DTYPE)
+    mats["base_color"] = [(0.9, 0.1, 0.1), (0.1, 0.9, 0.1)]
+    mats["roughness"] = 0.5
+    mats["ior"] = 1.5
+    nodes = np.zeros(3, bvr.BVH_NODE_DTYPE)
+    nodes["bounds_min"][:] = (-1.1, -1.1, -6.1)
+    nodes["bounds_max"][:] = (1.1, 1.1, -3.9)
+    nodes["index"][0], nodes["model_count"][0] = 1, 0
+    nodes["index"][1], nodes["model_count"][1] = 0, 1
+    nodes["index"][2], nodes["model_count"][2] = 1, 1
+    W, H = 16, 16
+    cam = bvr.make_camera(position=(0, 0, 0), target=(0, 0, -1), aspect=1.0, sample_count=1, bounces=1)
+    win = bvr.make_window(0.5, H)
+    tree, _ = oracle.render(models, mats, nodes, cam, bvr.make_level(3), win, W)
+    brute, _ = oracle.render(models, mats, nodes, cam, bvr.make_level(3), win, W, brute_force=True)
+    hit = tree["primary_id"] != 0xFFFFFFFF
+    assert hit.any() and np.array_equal(tree["primary_depth"], brute["primary_depth"])
+    assert (tree["primary_id"][hit] == 1).all()        # second leaf: popped first
+    assert (brute["primary_id"][hit] == 0).all()       # buffer order: first model first
+    ranks, _ = bvr.traversal_ranks(nodes, 2)
+    assert list(ranks) == [1, 0]
