@@ -7,12 +7,14 @@ CSRC := bevyray_b200/csrc
 CU_SRCS := $(wildcard $(CSRC)/*.cu)
 HOST_SRCS := $(wildcard $(CSRC)/host/*.cpp)
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/host/*.hpp) $(wildcard include/*.h)
-LIB := bevyray_b200/libbevyray_b200.so
+LIB ?= bevyray_b200/libbevyray_b200.so
+# compile-time variants for A/B runs: make LIB=/path/other.so DEFS="-DBVR_FAR_GENERIC=0"; BEVYRAY_B200_LIB picks it at run time
+DEFS ?=
 
 NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
 	--fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
 	-ccbin $(HOSTCXX) -Xcompiler -fPIC,-fopenmp,-ffp-contract=off,-fno-fast-math,-Wall \
-	-Xptxas -v
+	-Xptxas -v $(DEFS)
 
 all: $(LIB) oracle
 

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbevyray_b200.so")
+# BEVYRAY_B200_LIB: another build of the same library (A/B runs of compile-time variants); default = the in-tree build
+LIB_PATH = os.environ.get("BEVYRAY_B200_LIB") or os.path.join(_HERE, "libbevyray_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -33,6 +34,7 @@ RAYTRACING_SKIP, RAYTRACING_FALLBACK_RASTER, RAYTRACING_FALLBACK_RAYTRACED, RAYT
 KERNEL_AUTO, KERNEL_MEGAKERNEL, KERNEL_WAVEFRONT, KERNEL_CTA_WAVEFRONT = 0, 1, 2, 3
 TRAVERSAL_AUTO, TRAVERSAL_REFERENCE_ORDER = 0, 1
 ARRAY_MODELS, ARRAY_MATERIALS, ARRAY_BVH_NODES = 0, 1, 2
+RENDER_DEFER_COMPOSITE = 1
 
 
 class BvrModel(C.Structure):
@@ -71,7 +73,7 @@ class BvrDirtyRange(C.Structure):
 class BvrRenderOptions(C.Structure):
     _fields_ = [("width", C.c_uint32), ("kernel", C.c_uint32), ("traversal", C.c_uint32),
                 ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("strip_rows", C.c_uint32),
-                ("reserved", C.c_uint32 * 2)]
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class BvrOutputs(C.Structure):
@@ -106,6 +108,7 @@ SIGNATURES = {
     "bvr_last_error": (C.c_char_p, [_vp]),
     "bvr_set_stream": (_i, [_vp, _vp]),
     "bvr_sync": (_i, [_vp]),
+    "bvr_reload_tuning": (_i, [_vp]),
     "bvr_upload_scene": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
     "bvr_upload_scene_gpu_bvh": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
     "bvr_shard_rows": (_u32, [_u32, _P(BvrRenderOptions)]),
@@ -113,9 +116,11 @@ SIGNATURES = {
     "bvr_render": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _P(BvrWindow), _P(BvrRenderOptions), _vp, _vp, _P(BvrOutputs)]),
     "bvr_render_device": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _P(BvrWindow), _P(BvrRenderOptions), _vp, _vp, _P(BvrOutputs)]),
     "bvr_axpby_device": (_i, [_vp, _vp, _f, _vp, _f, _sz]),
+    "bvr_composite_device": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _vp, _vp, _vp, _vp, _sz]),
     "bvr_unshard_device": (_i, [_vp, _vp, _sz, _vp, _u32, _u32, _u32, _u32, _u32]),
     "bvr_get_stats": (_i, [_vp, _P(BvrStats)]),
     "bvr_bench_fp32_peak": (_i, [_i, _P(_f)]),
+    "bvr_bench_l2_bandwidth": (_i, [_i, _P(_f)]),
     # include/bevyray_b200_host.h
     "bvrh_scene_rtiow": (_vp, [_u64]),
     "bvrh_scene_random": (_vp, [_u64, _u32, _f, _f, _f]),

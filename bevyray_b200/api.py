@@ -165,6 +165,10 @@ class Context:
     def sync(self):
         self._check(lib.bvr_sync(self._h))
 
+    def reload_tuning(self):
+        """Re-reads the BVR_* experiment knobs from the environment (they are otherwise read once, at creation)."""
+        self._check(lib.bvr_reload_tuning(self._h))
+
     def upload_scene(self, models, materials, nodes, ranges=None):
         models = np.ascontiguousarray(models, dtype=MODEL_DTYPE)
         materials = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
@@ -231,7 +235,12 @@ class Context:
                                           C.c_void_p(d_raster_rgba or None), C.c_void_p(d_raster_depth or None), C.byref(o)))
 
     def axpby_device(self, d_dst, dst_weight, d_src, src_weight, n):
-        self._check(lib.bvr_axpby_device(self._h, C.c_void_p(d_dst), dst_weight, C.c_void_p(d_src), src_weight, n))
+        self._check(lib.bvr_axpby_device(self._h, C.c_void_p(d_dst), dst_weight, C.c_void_p(d_src or None), src_weight, n))
+
+    def composite_device(self, camera, level, d_rgba, d_rt_depth, d_raster_rgba, d_raster_depth, n_pixels):
+        lv = level if isinstance(level, capi.BvrRaytraceLevel) else make_level(level)
+        self._check(lib.bvr_composite_device(self._h, C.byref(camera), C.byref(lv), C.c_void_p(d_rgba), C.c_void_p(d_rt_depth),
+                                             C.c_void_p(d_raster_rgba or None), C.c_void_p(d_raster_depth or None), n_pixels))
 
     def unshard_device(self, d_gathered, shard_stride_words, d_full, width, height, channels, shard_count, strip_rows):
         self._check(lib.bvr_unshard_device(self._h, C.c_void_p(d_gathered), shard_stride_words, C.c_void_p(d_full),

@@ -21,7 +21,66 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters, f
     if (s == 123456.789f) out[0] = s;   // never true; keeps the chains alive
 }
 
+// L2 -> SM read bandwidth: every CTA streams the whole buffer (far larger than L1, smaller than L2) with 128-bit
+// .cg loads (cached in L2 only), CTAs starting at staggered offsets so that all L2 slices are busy at once.
+__global__ void __launch_bounds__(512) l2_probe_kernel(const uint4* __restrict__ buf, size_t n_vec, int passes, uint32_t* out) {
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    const size_t start = ((size_t)blockIdx.x * 7919u * 512u) % n_vec;
+    for (int p = 0; p < passes; p++) {
+        for (size_t base = 0; base < n_vec; base += (size_t)512u * 4u) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                size_t i = start + base + (size_t)u * 512u + threadIdx.x;
+                if (i >= n_vec) i -= n_vec;
+                const uint4 v = __ldcg(buf + i);
+                acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+            }
+        }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) out[0] = acc.x;   // practically never; keeps the loads alive
+}
+
 }  // namespace
+
+// L2 -> SM bandwidth in GB/s: the roofline denominator for scenes walked out of L2 (BASELINE configs[3]).
+extern "C" int bvr_bench_l2_bandwidth(int device, float* gbs_out) {
+    if (!gbs_out) return BVR_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return BVR_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return BVR_ERR_CUDA; }
+    const size_t bytes = (size_t)32 << 20;            // 32 MiB: a quarter of the 126 MB L2, 140x the L1
+    const size_t n_vec = bytes / sizeof(uint4);
+    uint4* buf = nullptr;
+    uint32_t* out = nullptr;
+    if (cudaMalloc(&buf, bytes) != cudaSuccess || cudaMalloc(&out, 4) != cudaSuccess) {
+        cudaGetLastError();
+        if (buf) cudaFree(buf);
+        return BVR_ERR_OUT_OF_MEMORY;
+    }
+    cudaMemset(buf, 0x5a, bytes);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 2, passes = 2;
+    float best = 0.0f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        l2_probe_kernel<<<blocks, 512>>>(buf, n_vec, passes, out);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); cudaFree(buf); cudaFree(out); return BVR_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double moved = (double)bytes * passes * blocks;
+        const float gbs = (float)(moved / (ms * 1e-3) / 1e9);
+        if (rep > 0 && gbs > best) best = gbs;       // rep 0 brings the buffer into L2
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(out);
+    *gbs_out = best;
+    return BVR_OK;
+}
 
 extern "C" int bvr_bench_fp32_peak(int device, float* tflops_out) {
     if (!tflops_out) return BVR_ERR_INVALID_ARGUMENT;

@@ -50,8 +50,16 @@ struct PinnedBuffer {
 
 }  // namespace
 
+// Tuning knobs for experiments, read from the environment ONCE per context (bvr_create) and again
+// only on request (bvr_reload_tuning); production uses the defaults.
+struct EnvTuning {
+    int no_tight = 0, tight_pad = 100, no_q16 = 0, no_bvh4 = 0, gpu_validate = -1, wf_refill = 8;
+    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0;
+};
+
 struct BvrContext {
     int device = 0;
+    EnvTuning tune;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string error;
@@ -75,11 +83,11 @@ struct BvrContext {
     bool has_scene = false;
     uint32_t root_ref_host = 0;
     uint32_t tree_depth = 0;
+    bool tree_is_ours = false;                // built by bvr_upload_scene_gpu_bvh: the reference never saw this tree
     uint32_t n_inner = 0;
     uint32_t max_leaf_models = 0;
     int sm_count = 0;
     DeviceBuffer pixel_counter;
-    DeviceBuffer px_acc;                      // per-pixel accumulators of the v5 experiment
     DeviceBuffer wf_state;
     DeviceBuffer bvh_scratch;
     unsigned int* depth_host = nullptr;       // pinned
@@ -124,10 +132,26 @@ bool is_pinned_host(const void* p) {
     return attr.type == cudaMemoryTypeHost;
 }
 
-// tuning knobs for experiments (documented in DESIGN.md); production uses the defaults
 int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
+}
+
+EnvTuning read_env_tuning() {
+    EnvTuning t;
+    t.no_tight = env_int("BVR_NO_TIGHT", 0);
+    t.tight_pad = env_int("BVR_TIGHT_PAD", 100);
+    t.no_q16 = env_int("BVR_NO_Q16", 0);
+    t.no_bvh4 = env_int("BVR_NO_BVH4", 0);
+    t.gpu_validate = env_int("BVR_GPU_VALIDATE", -1);
+    t.wf_refill = env_int("BVR_WF_REFILL", 8);
+    t.mk_v1 = env_int("BVR_MK_V1", 0);
+    t.mk_threads = env_int("BVR_MK_THREADS", 0);
+    t.mk_wait = env_int("BVR_MK_WAIT", 0);
+    t.mk_leaf = env_int("BVR_MK_LEAF", 0);
+    t.selfcheck = env_int("BVR_SELFCHECK", 0);
+    t.no_top = env_int("BVR_NO_TOP", 0);
+    return t;
 }
 
 uint32_t effective_strip_rows(const BvrRenderOptions* o) { return (o && o->strip_rows) ? o->strip_rows : 8u; }
@@ -142,8 +166,11 @@ uint32_t shard_rows_impl(uint32_t height, const BvrRenderOptions* o) {
 }
 
 // Host-side structural validation of the node array against the reference contract
-// (raytrace.wgsl:80-87, 313-346): everything reachable from node 0 exactly once, indices in range.
-// Also yields the tree depth (stack bound for the near-first traversal).
+// (raytrace.wgsl:80-87, 313-346).  EVERY node of the array is range-checked and may be referenced at most once —
+// the derive kernels (scene_kernels.cu) run over all nodes, reachable or not, and the GPU validator
+// (scene_validate.cu: gv_link) applies the same rule, so both paths accept and reject the same arrays.
+// The walk from node 0 then yields the tree depth (stack bound) and the reference's order over the leaves.
+// n_inner counts ALL inner nodes of the array: it sizes the derived record arrays.
 int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, size_t n_materials,
                    const BvrBvhNode* nodes, size_t n_nodes, uint32_t* depth_out, uint32_t* n_inner_out,
                    uint32_t* max_leaf_out, std::vector<uint32_t>* rank_out) {
@@ -158,9 +185,23 @@ int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, siz
     if (n_nodes == 0) return BVR_OK;
     if (n_nodes >= 0x7fffffffull) return fail(ctx, BVR_ERR_BAD_SCENE, "too many BVH nodes");
     std::vector<uint8_t> seen(n_nodes, 0);
+    for (size_t i = 0; i < n_nodes; i++) {
+        const BvrBvhNode& nd = nodes[i];
+        if (nd.model_count > 0) {
+            if (nd.model_count > BVR_MAX_LEAF_COUNT) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf with more than 128 models");
+            if ((size_t)nd.index + nd.model_count > n_models) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf model range out of bounds");
+        } else {
+            (*n_inner_out)++;
+            if ((size_t)nd.index + 1 >= n_nodes) return fail(ctx, BVR_ERR_BAD_SCENE, "child index out of bounds");
+            for (uint32_t c = nd.index; c < nd.index + 2; c++) {
+                // node 0 is the root: a reference to it closes a cycle
+                if (c == 0u || seen[c]) return fail(ctx, BVR_ERR_BAD_SCENE, "BVH node referenced twice (cycle or DAG)");
+                seen[c] = 1;
+            }
+        }
+    }
     std::vector<std::pair<uint32_t, uint32_t>> stack;   // (node, depth)
     stack.push_back({0u, 1u});
-    seen[0] = 1;
     uint32_t max_depth = 0;
     while (!stack.empty()) {
         const auto [i, d] = stack.back();
@@ -168,20 +209,13 @@ int validate_scene(BvrContext* ctx, const BvrModel* models, size_t n_models, siz
         if (d > max_depth) max_depth = d;
         const BvrBvhNode& nd = nodes[i];
         if (nd.model_count > 0) {
-            if (nd.model_count > BVR_MAX_LEAF_COUNT) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf with more than 128 models");
-            if ((size_t)nd.index + nd.model_count > n_models) return fail(ctx, BVR_ERR_BAD_SCENE, "leaf model range out of bounds");
             if (nd.model_count > *max_leaf_out) *max_leaf_out = nd.model_count;
             // this walk pops index+1 before index, like raytrace.wgsl:329-341: leaves come off in the reference's order
             for (uint32_t m = nd.index; m < nd.index + nd.model_count; m++)
                 if ((*rank_out)[m] == 0xffffffffu) (*rank_out)[m] = next_rank++;
         } else {
-            (*n_inner_out)++;
-            if ((size_t)nd.index + 1 >= n_nodes) return fail(ctx, BVR_ERR_BAD_SCENE, "child index out of bounds");
-            for (uint32_t c = nd.index; c < nd.index + 2; c++) {
-                if (seen[c]) return fail(ctx, BVR_ERR_BAD_SCENE, "BVH node referenced twice (cycle or DAG)");
-                seen[c] = 1;
-                stack.push_back({c, d + 1});
-            }
+            // (every node has at most one parent and node 0 none, so this walk is over a tree: it terminates)
+            for (uint32_t c = nd.index; c < nd.index + 2; c++) stack.push_back({c, d + 1});
         }
     }
     *depth_out = max_depth;
@@ -209,7 +243,7 @@ int derive_q16(BvrContext* ctx, size_t n_models, size_t n_nodes, uint32_t n_inne
     ctx->q16_built = false;
     ctx->q16_pending = false;
     ctx->nodes4_ch_built = false;
-    if (n_inner >= 1u && n_inner <= 1024u && n_models <= 1024u && max_leaf <= 1u) {
+    if (n_inner >= 1u && n_inner <= 1024u && n_models <= 1023u && max_leaf <= 1u) {   // 11-bit refs, 0x7ff = none
         BVR_CK(ctx->nodes4_ch.ensure((size_t)n_inner * 112u));
         *launches += launch_derive_nodes4_ch(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
                                              ctx->pairs_ch.as<float4>(), ctx->nodes4_ch.as<float4>(), ctx->stream);
@@ -217,14 +251,14 @@ int derive_q16(BvrContext* ctx, size_t n_models, size_t n_nodes, uint32_t n_inne
         // tight boxes: pad 0.01 instead of the reference's 0.1; rays that start too far from the spheres for
         // the tight boxes to be safe walk the reference records (scene_kernels.cu)
         ctx->tight_built = false;
-        if (!env_int("BVR_NO_TIGHT", 0) && n_nodes <= 2047u) {
+        if (!ctx->tune.no_tight && n_nodes <= 2047u) {
             BVR_CK(ctx->raw_nodes_tight.ensure(n_nodes * sizeof(RawNode)));
             BVR_CK(ctx->pairs_tight.ensure(n_nodes * 2 * sizeof(float4)));
             BVR_CK(ctx->pairs_ch_tight.ensure(n_nodes * 2 * sizeof(float4)));
             BVR_CK(ctx->nodes4_tight.ensure((size_t)n_inner * 112u));
             BVR_CK(ctx->tight_groups.ensure(33 * sizeof(float4)));
             *launches += launch_derive_tight(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->spheres.as<float4>(),
-                                             (uint32_t)n_models, 1e-4f * (float)env_int("BVR_TIGHT_PAD", 100), ctx->tight_groups.as<float4>(),
+                                             (uint32_t)n_models, 1e-4f * (float)ctx->tune.tight_pad, ctx->tight_groups.as<float4>(),
                                              ctx->raw_nodes_tight.as<RawNode>(), ctx->stream);
             *launches += launch_derive_pairs(ctx->raw_nodes_tight.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
                                              ctx->block_sums.as<uint32_t>(), ctx->pairs_tight.as<float4>(),
@@ -235,7 +269,7 @@ int derive_q16(BvrContext* ctx, size_t n_models, size_t n_nodes, uint32_t n_inne
         }
     }
     const size_t scene_bytes = (size_t)n_inner * 64u + n_models * 20u;
-    if (env_int("BVR_NO_Q16", 0) || scene_bytes <= 160u * 1024u || n_inner > (1u << 20) || n_models > (1u << 20) || max_leaf > 1u)
+    if (ctx->tune.no_q16 || scene_bytes <= 160u * 1024u || n_inner > (1u << 20) || n_models > (1u << 20) || max_leaf > 1u)
         return BVR_OK;
     BVR_CK(ctx->pairs_q.ensure((size_t)n_inner * 32u + 32u));
     BVR_CK(ctx->qgrid.ensure(16 * sizeof(float)));
@@ -306,6 +340,7 @@ int bvr_create(int device, BvrContext** out_ctx) {
     }
     *ctx->ray_counter_host = 0;
     ctx->stream = ctx->own_stream;
+    ctx->tune = read_env_tuning();
     *out_ctx = ctx;
     return BVR_OK;
 }
@@ -317,7 +352,7 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->pairs_ch, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->px_acc, &ctx->validate_scratch, &ctx->validate_out, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->validate_scratch, &ctx->validate_out, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
@@ -341,6 +376,12 @@ int bvr_set_stream(BvrContext* ctx, void* cuda_stream) {
     cudaSetDevice(ctx->device);
     BVR_CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return BVR_OK;
+}
+
+int bvr_reload_tuning(BvrContext* ctx) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->tune = read_env_tuning();
     return BVR_OK;
 }
 
@@ -372,7 +413,7 @@ int bvr_upload_scene(BvrContext* ctx,
 
     // Small trees are validated on the host before anything is touched; big ones on the GPU, on the uploaded bytes
     // (scene_validate.cu: the host walk costs 80 ms for 2 M nodes).  BVR_GPU_VALIDATE=0/1 forces either.
-    const int gv_env = env_int("BVR_GPU_VALIDATE", -1);
+    const int gv_env = ctx->tune.gpu_validate;
     bool gpu_validate = n_nodes > 0 && (gv_env >= 0 ? gv_env != 0 : n_nodes >= 32768u);
     uint32_t depth = ctx->tree_depth, n_inner = ctx->n_inner, max_leaf = ctx->max_leaf_models;
     std::vector<uint32_t> rank;
@@ -498,6 +539,7 @@ int bvr_upload_scene(BvrContext* ctx,
     ctx->tree_depth = depth;
     ctx->n_inner = n_inner;
     ctx->max_leaf_models = max_leaf;
+    if (nodes_dirty || !partial) ctx->tree_is_ours = false;
     ctx->has_scene = n_nodes > 0 && n_models > 0;
     ctx->scene_uploaded = true;
     return BVR_OK;
@@ -596,6 +638,7 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
     ctx->tree_depth = *ctx->depth_host;
     ctx->n_inner = n_models ? (uint32_t)(n_models - 1) : 0u;
     ctx->max_leaf_models = n_models ? 1u : 0u;   // the GPU builder emits one sphere per leaf
+    ctx->tree_is_ours = true;
     ctx->root_ref_host = (n_models == 1) ? (BVR_LEAF_BIT | 0u) : 0u;
     ctx->has_scene = n_models > 0;
     ctx->scene_uploaded = true;
@@ -636,9 +679,9 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     p.scene.sphere_material = ctx->sphere_material.as<uint32_t>();
     p.scene.materials = ctx->raw_materials.as<float4>();
     p.scene.model_rank = ctx->n_models ? ctx->model_rank.as<uint32_t>() : nullptr;
-    if (ctx->nodes4_ch_built && !env_int("BVR_NO_BVH4", 0)) {
+    if (ctx->nodes4_ch_built && !ctx->tune.no_bvh4) {
         p.scene.nodes4_ch = ctx->nodes4_ch.as<float4>();
-        if (ctx->tight_built && !env_int("BVR_NO_TIGHT", 0)) {
+        if (ctx->tight_built && !ctx->tune.no_tight) {
             p.scene.nodes4_tight = ctx->nodes4_tight.as<float4>();
             p.scene.tight_groups = ctx->tight_groups.as<float4>();
         }
@@ -647,7 +690,7 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
         if (ctx->q16_pending) { BVR_CK(cudaEventSynchronize(ctx->q16_done)); ctx->q16_pending = false; }
         if (*ctx->q16_bad_host == 0u) {
             p.scene.pairs_q = ctx->pairs_q.as<uint4>();
-            p.scene.nodes4_q = env_int("BVR_NO_BVH4", 0) ? nullptr : ctx->nodes4_q.as<uint4>();
+            p.scene.nodes4_q = ctx->tune.no_bvh4 ? nullptr : ctx->nodes4_q.as<uint4>();
             p.scene.qgrid = ctx->qgrid.as<float>();
         }
     }
@@ -680,7 +723,9 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     c.seed_scaled = window->random_seed * 10000.0f;
     c.sample_count = camera->sample_count;
     c.bounce_count = camera->bounce_count;
-    c.level = level->level;
+    // BVR_RENDER_DEFER_COMPOSITE: the kernels skip the depth composite (they see level Pure) but keep the level's
+    // fallback depth for misses (raytrace.wgsl:177-182); bvr_composite_device applies it later
+    c.level = (opts->flags & BVR_RENDER_DEFER_COMPOSITE) && level->level != 0u ? 3u : level->level;
     c.width = opts->width;
     c.height = window->height;
 
@@ -689,8 +734,14 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     p.shard.strip_rows = p.shard.count > 1 ? effective_strip_rows(opts) : window->height;
     p.shard.rows = shard_rows_impl(window->height, opts);
     p.ray_counter = ctx->ray_counter.as<unsigned long long>();
-    // the near-first stack holds one entry per level; deeper trees use the reference-order traversal
-    p.reference_order = (opts->traversal == BVR_TRAVERSAL_REFERENCE_ORDER || ctx->tree_depth + 1 > BVR_FAST_STACK) ? 1u : 0u;
+    // The reference abandons a traversal when its stack index reaches 32 (raytrace.wgsl:320), which a tree of 32 or
+    // more levels can trigger (an inner node on level k leaves k+1 entries when both children are entered).  For an
+    // UPLOADED tree that deep the verbatim reference-order kernel runs, truncation included, so the image stays the
+    // reference's.  A tree the library built itself (bvr_upload_scene_gpu_bvh) was never seen by the reference:
+    // truncating there would only lose hits, so it is always walked completely (near-first, one stack entry per level).
+    const bool may_truncate = ctx->tree_depth >= BVR_REF_STACK;
+    p.reference_order = (opts->traversal == BVR_TRAVERSAL_REFERENCE_ORDER || (may_truncate && !ctx->tree_is_ours) ||
+                         ctx->tree_depth + 1 > BVR_FAST_STACK) ? 1u : 0u;
     *out = p;
     return BVR_OK;
 }
@@ -728,7 +779,7 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
             std::memset(&w, 0, sizeof w);
             w.r = p;
             wavefront_bind(w, ctx->wf_state.ptr, slots);
-            w.refill_below = (uint32_t)env_int("BVR_WF_REFILL", 8);
+            w.refill_below = (uint32_t)ctx->tune.wf_refill;
             if (cta) {
                 BVR_CK(cudaMemsetAsync(ctx->pixel_counter.ptr, 0, sizeof(unsigned int), ctx->stream));
                 n = launch_cta_wavefront(w, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth, ctx->sm_count,
@@ -742,42 +793,18 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
                 if (e != cudaSuccess) return fail_cuda(ctx, e, "wavefront pipeline");
             }
         }
-        if (n < 0 && !p.reference_order && !env_int("BVR_MK_V1", 0)) {
+        if (n < 0 && !p.reference_order && !ctx->tune.mk_v1) {
             BVR_CK(cudaMemsetAsync(ctx->pixel_counter.ptr, 0, sizeof(unsigned int), ctx->stream));
             // largest CTA whose stacks (and, when it fits, the scene) fit in shared memory
-            const int forced = env_int("BVR_MK_THREADS", 0);
-            const int variant = env_int("BVR_MK_VARIANT", 3);
-            if (variant == 4) {
-                // two paths per lane; scenes it does not take (see megakernel_v4.cu) fall through to v3
-                const int cand4[3] = {768, 640, 512};
-                for (int ci = 0; ci < 3 && n < 0; ci++) {
-                    const int threads = forced ? forced : cand4[ci];
-                    n = launch_megakernel_v4(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth, ctx->max_leaf_models,
-                                             ctx->pixel_counter.as<unsigned int>(), threads,
-                                             (uint32_t)env_int("BVR_MK4_SHADE", 24), (uint32_t)env_int("BVR_MK4_STUCK", 6),
-                                             (uint32_t)env_int("BVR_MK4_SWITCH", 6), (uint32_t)env_int("BVR_MK_LEAF", 4),
-                                             ctx->sm_count, ctx->stream);
-                    if (forced) break;
-                }
-                if (n < 0) cudaGetLastError();
-            }
-            if (variant == 5) {
-                BVR_CK(ctx->px_acc.ensure((size_t)p.cam.width * p.shard.rows * sizeof(float4)));
-                n = launch_megakernel_v5(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
-                                         ctx->pixel_counter.as<unsigned int>(), ctx->px_acc.as<float4>(),
-                                         (uint32_t)env_int("BVR_MK5_SHADERS", 8), (uint32_t)env_int("BVR_MK5_SWAP", 8),
-                                         (uint32_t)env_int("BVR_MK5_EXTRA", 192), (uint32_t)env_int("BVR_MK5_BATCH", 24),
-                                         ctx->sm_count, ctx->stream);
-                if (n < 0) cudaGetLastError();
-            }
+            const int forced = ctx->tune.mk_threads;
             const int candidates[4] = {1024, 768, 512, 256};
             for (int ci = 0; ci < 4 && n < 0; ci++) {
-                const int threads = (forced && variant != 4) ? forced : candidates[ci];
+                const int threads = forced ? forced : candidates[ci];
                 n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
                                          ctx->pixel_counter.as<unsigned int>(), threads,
-                                         (uint32_t)env_int("BVR_MK_WAIT", 0), (uint32_t)env_int("BVR_MK_LEAF", 0),   // 0 = per-mode default
+                                         (uint32_t)ctx->tune.mk_wait, (uint32_t)ctx->tune.mk_leaf,   // 0 = per-mode default
                                          ctx->sm_count, ctx->stream);
-                if (forced && variant != 4) break;
+                if (forced) break;
             }
             if (n < 0) cudaGetLastError();
         }
@@ -816,7 +843,8 @@ int bvr_render(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel*
     cudaSetDevice(ctx->device);
     const size_t full_px = (size_t)opts->width * window->height;
     const size_t shard_px = (size_t)opts->width * shard_rows_impl(window->height, opts);
-    const bool need_rgba = level->level <= 2u, need_depth = level->level == 1u || level->level == 2u;
+    const uint32_t eff_level = ((opts->flags & BVR_RENDER_DEFER_COMPOSITE) && level->level != 0u) ? 3u : level->level;
+    const bool need_rgba = eff_level <= 2u, need_depth = eff_level == 1u || eff_level == 2u;
     if (need_rgba && !raster_rgba) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "levels 0-2 need the raster colour");
     if (need_depth && !raster_depth) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "levels 1-2 need the raster depth");
 
@@ -883,9 +911,29 @@ int bvr_render(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel*
 int bvr_axpby_device(BvrContext* ctx, float* d_dst, float dst_weight, const float* d_src, float src_weight, size_t n) {
     if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
     ctx->error.clear();
-    if (n && (!d_dst || !d_src)) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null device pointer");
+    if (n && (!d_dst || (!d_src && src_weight != 0.0f))) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null device pointer");
     cudaSetDevice(ctx->device);
     ctx->stats.kernel_launches += (uint64_t)launch_axpby(d_dst, dst_weight, d_src, src_weight, n, ctx->stream);
+    BVR_CK(cudaGetLastError());
+    return BVR_OK;
+}
+
+int bvr_composite_device(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level, float* d_rgba,
+                         const float* d_rt_depth, const float* d_raster_rgba, const float* d_raster_depth, size_t n_pixels) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    if (!camera || !level) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null uniform pointer");
+    if (level->level != 1u && level->level != 2u) return BVR_OK;   // levels 0 and 3 have no depth test (raytrace.wgsl:97-122)
+    if (n_pixels && (!d_rgba || !d_rt_depth || !d_raster_rgba || !d_raster_depth))
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null device pointer");
+    cudaSetDevice(ctx->device);
+    CameraParams c;
+    std::memset(&c, 0, sizeof c);
+    c.near_plane = camera->near_plane;
+    c.far_plane = camera->far_plane;
+    ctx->stats.kernel_launches += (uint64_t)launch_composite(reinterpret_cast<float4*>(d_rgba), d_rt_depth,
+                                                             reinterpret_cast<const float4*>(d_raster_rgba), d_raster_depth,
+                                                             c, n_pixels, ctx->stream);
     BVR_CK(cudaGetLastError());
     return BVR_OK;
 }

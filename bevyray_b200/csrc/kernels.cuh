@@ -111,16 +111,6 @@ int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple o
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
                          int sm_count, cudaStream_t stream);
-// two-paths-per-lane megakernel (v4); -1 when the scene does not qualify (see megakernel_v4.cu) -> use v3
-int launch_megakernel_v4(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
-                         uint32_t max_leaf_models, unsigned int* pixel_counter, int threads, uint32_t shade_lanes,
-                         uint32_t stuck_lanes, uint32_t switch_lanes, uint32_t leaf_batch_lanes, int sm_count,
-                         cudaStream_t stream);
-// warp-specialised kernel with a per-CTA ray pool (v5, experiment); -1 when the scene does not qualify -> use v3.
-// px_acc: one float4 per shard pixel (accumulators live in HBM/L2)
-int launch_megakernel_v5(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
-                         unsigned int* pixel_counter, float4* px_acc, uint32_t shader_warps, uint32_t swap_lanes,
-                         uint32_t extra_paths, uint32_t min_batch, int sm_count, cudaStream_t stream);
 size_t wavefront_state_bytes(size_t slots);
 void wavefront_bind(WavefrontParams& w, void* state, size_t slots);
 // persistent per-CTA wavefront (cta_wavefront.cu): number of path slots it needs, and the launch
@@ -134,6 +124,8 @@ int launch_copy_raster(const RenderParams& p, cudaStream_t stream);   // level 0
 
 // ---- multi-GPU helpers (shard_kernels.cu) ----
 int launch_axpby(float* dst, float dst_weight, const float* src, float src_weight, size_t n, cudaStream_t stream);
+int launch_composite(float4* rgba, const float* rt_depth, const float4* raster_rgba, const float* raster_depth,
+                     const CameraParams& cam, size_t n, cudaStream_t stream);
 int launch_unshard(const uint32_t* gathered, size_t shard_stride_words, uint32_t* full, uint32_t width,
                    uint32_t height, uint32_t channels, uint32_t shard_count, uint32_t strip_rows,
                    cudaStream_t stream);

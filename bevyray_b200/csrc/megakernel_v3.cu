@@ -27,6 +27,9 @@ enum LaneState : int { NEED_PIXEL = 0, NEW_PATH = 1, RAY_READY = 2, TRAVERSE = 3
 enum Kind : int { K_NONE = 0, K_MISS = 1, K_METAL = 2, K_GLASS = 3, K_DIFFUSE = 4 };
 
 #define V3_NONE 0x7fffffffu
+#ifndef BVR_FAR_GENERIC
+#define BVR_FAR_GENERIC 1      // MODE 5: far rays pick their records through a generic pointer (no predicated second load path)
+#endif
 #ifndef BVR_STEPS_PER_VOTE
 #define BVR_STEPS_PER_VOTE 2   // traversal steps between two rounds of warp votes
 #endif
@@ -71,6 +74,24 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t a) {
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
+
+// Packed fp32 pairs (sm_100: FFMA2 = two IEEE fp32 FMAs per issued instruction).  ptxas folds the negation and the
+// absolute value of a pair operand into the instruction, and reads a (z, z) pair as one broadcast register.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// hides how a value was computed, so that the compiler keeps it in a register instead of re-deriving it in the
+// traversal loop (the shared-window base costs an S2R + LEA per use otherwise: profiles/r01 SASS)
+__device__ __forceinline__ uint32_t opaque(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 
 // Culling-only slab test on (centre, half extent) boxes.  Per axis: tc = fma(c, 1/d, -o/d), th = h * |1/d|,
 // lo = tc - th, hi = tc + th — four FMA-pipe instructions instead of two FFMA + two FMNMX: the traversal loop is
@@ -125,7 +146,7 @@ __device__ __forceinline__ uint32_t sort4_park(uint32_t k0, uint32_t k1, uint32_
 }
 
 #define S4_LEAF 0x400u
-#define S4_NONE 0x800u
+#define S4_NONE 0x7ffu      // == (0xffffffff & S4_REF_MASK): a key that was not entered decodes to NONE by itself
 #define S4_REF_MASK 0x7ffu
 #define Q16_LEAF 0x100000u
 #define Q16_NONE 0x200000u
@@ -182,7 +203,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     }
     // per-lane stack: entry k of lane t at s_stack0 + k * STACK_STRIDE (interleaved: conflict-free)
     constexpr uint32_t STACK_STRIDE = THREADS * (STACK4 ? 4u : 8u);
-    const uint32_t s_stack0 = smem_addr(sm_cursor) + tid * (STACK4 ? 4u : 8u);
+    const uint32_t s_stack0 = opaque(smem_addr(sm_cursor) + tid * (STACK4 ? 4u : 8u));
     // MODE 2: the quantisation grid and the root in 21-bit form
     const float qbx = Q16 ? sv.qgrid[0] : 0.f, qby = Q16 ? sv.qgrid[1] : 0.f, qbz = Q16 ? sv.qgrid[2] : 0.f;
     const float qsx = Q16 ? sv.qgrid[4] : 0.f, qsy = Q16 ? sv.qgrid[5] : 0.f, qsz = Q16 ? sv.qgrid[6] : 0.f;
@@ -193,7 +214,8 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     uint32_t snx = 0, sny = 0, snz = 0, sfx = 0, sfy = 0, sfz = 0;   // MODE 2: PRMT selectors of the near / far halves
     const uint32_t n_groups = TIGHT ? __float_as_uint(__ldg(&sv.tight_groups[0]).x) : 0u;
     bool far_ray = false;   // MODE 5: this ray walks the reference boxes
-    const uint32_t s_pairs = SMEM_SCENE ? smem_addr(sv.pairs_ch) : 0u;
+    const uint32_t s_pairs = SMEM_SCENE ? opaque(smem_addr(sv.pairs_ch)) : 0u;
+    const float4* const g_pairs = sv.pairs_ch;   // MODE 5: the staged tight records through a generic pointer
 
     const uint32_t tiles_x = (cam.width + 7u) / 8u, tiles_y = (p.shard.rows + 3u) / 4u;
     const uint32_t total_slots = tiles_x * tiles_y * 32u;
@@ -207,6 +229,8 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     V3 throughput = v3(1.0f, 1.0f, 1.0f);
     Ray ray{v3(0, 0, 0), v3(0, 0, 1)};
     V3 inv = v3(0, 0, 0), ainv = v3(0, 0, 0), noi = v3(0, 0, 0);
+    u64 inv_xy = 0, noi_xy = 0;                  // S4: (x, y) of 1/d and of -o/d as one register pair (FFMA2 operands)
+    const float4* rec_base = g_pairs;            // MODE 5: records this ray walks (shared tight / global reference)
     float a = 1.0f;
     Hit closest{BVR_INF, 0xffffffffu};
     uint32_t cur = NONE, pending = NONE;
@@ -395,6 +419,10 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 const V3 bo = v3((qbx - ray.o.x) * inv.x, (qby - ray.o.y) * inv.y, (qbz - ray.o.z) * inv.z);
                 inv = v3(qsx * inv.x, qsy * inv.y, qsz * inv.z);
                 noi = v3(__fmaf_rn(-8388608.0f, inv.x, bo.x), __fmaf_rn(-8388608.0f, inv.y, bo.y), __fmaf_rn(-8388608.0f, inv.z, bo.z));
+            } else if (S4) {
+                inv_xy = pk2(inv.x, inv.y);
+                noi_xy = pk2(-(ray.o.x * inv.x), -(ray.o.y * inv.y));
+                noi.z = -(ray.o.z * inv.z);
             } else {
                 ainv = v3(fabsf(inv.x), fabsf(inv.y), fabsf(inv.z));
                 noi = v3(-(ray.o.x * inv.x), -(ray.o.y * inv.y), -(ray.o.z * inv.z));
@@ -406,6 +434,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                     const float dx = ray.o.x - gr.x, dy = ray.o.y - gr.y, dz = ray.o.z - gr.z;
                     far_ray = far_ray || !(dx * dx + dy * dy + dz * dz <= gr.w);
                 }
+                rec_base = far_ray ? sv.nodes4_ch : g_pairs;
             }
             a = vdot(ray.d, ray.d);
             closest.t = BVR_INF;
@@ -426,29 +455,49 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                     uint32_t c = cur;
                     if (Q16 ? c < Q16_LEAF : (S4 ? c < S4_LEAF : c < V3_NONE)) {  // inner node: test its children
                         if constexpr (S4) {
-                            // four children in shared memory: key = 21 bits of entry distance | 11 bits of ref
-                            const uint32_t na = s_pairs + c * 112u;
+                            // four children: key = 21 bits of entry distance | 11 bits of ref.  Record layout (scene_kernels.cu):
+                            // q0..q3 = (c.x, c.y, h.x, h.y) of child 0..3, q4 / q5 = (c.z, c.z', h.z, h.z') of children 0,1 / 2,3.
                             float4 q0, q1, q2, q3, q4, q5, rr;
-                            if (TIGHT && far_ray) {
+                            if constexpr (TIGHT && BVR_FAR_GENERIC) {
+                                // one generic pointer per ray: LD resolves the shared / global window itself
+                                const float4* nd = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(rec_base) + c * 112u);
+                                q0 = nd[0]; q1 = nd[1]; q2 = nd[2]; q3 = nd[3]; q4 = nd[4]; q5 = nd[5]; rr = nd[6];
+                            } else if (TIGHT && far_ray) {
                                 const float4* nd = sv.nodes4_ch + 7u * c;
                                 q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2); q3 = __ldg(nd + 3);
                                 q4 = __ldg(nd + 4); q5 = __ldg(nd + 5); rr = __ldg(nd + 6);
                             } else {
+                                const uint32_t na = s_pairs + c * 112u;
                                 q0 = lds128(na); q1 = lds128(na + 16u); q2 = lds128(na + 32u);
                                 q3 = lds128(na + 48u); q4 = lds128(na + 64u); q5 = lds128(na + 80u);
                                 rr = lds128(na + 96u);
                             }
-                            float e;
-                            uint32_t k0 = box_cull(inv, ainv, noi, closest.t, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, e)
-                                              ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.x)) : 0xffffffffu;
-                            uint32_t k1 = box_cull(inv, ainv, noi, closest.t, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, e)
-                                              ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.y)) : 0xffffffffu;
-                            uint32_t k2 = box_cull(inv, ainv, noi, closest.t, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, e)
-                                              ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.z)) : 0xffffffffu;
-                            uint32_t k3 = box_cull(inv, ainv, noi, closest.t, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, e)
-                                              ? ((__float_as_uint(e) & ~S4_REF_MASK) | __float_as_uint(rr.w)) : 0xffffffffu;
+                            // per axis pair: tc = c/d - o/d, lo = tc - h |1/d|, hi = tc + h |1/d|: 18 FFMA2 for four boxes
+                            float ix, iy;
+                            upk2(inv_xy, ix, iy);
+                            const u64 a_xy = pk2(fabsf(ix), fabsf(iy));
+                            const u64 i_zz = pk2(inv.z, inv.z), n_zz = pk2(noi.z, noi.z), a_zz = pk2(fabsf(inv.z), fabsf(inv.z));
+                            const u64 t0 = ffma2(pk2(q0.x, q0.y), inv_xy, noi_xy), t1 = ffma2(pk2(q1.x, q1.y), inv_xy, noi_xy);
+                            const u64 t2 = ffma2(pk2(q2.x, q2.y), inv_xy, noi_xy), t3 = ffma2(pk2(q3.x, q3.y), inv_xy, noi_xy);
+                            const u64 tz01 = ffma2(pk2(q4.x, q4.y), i_zz, n_zz), tz23 = ffma2(pk2(q5.x, q5.y), i_zz, n_zz);
+                            float lx0, ly0, lx1, ly1, lx2, ly2, lx3, ly3, lz0, lz1, lz2, lz3;
+                            float hx0, hy0, hx1, hy1, hx2, hy2, hx3, hy3, hz0, hz1, hz2, hz3;
+                            upk2(ffma2(pk2(-q0.z, -q0.w), a_xy, t0), lx0, ly0); upk2(ffma2(pk2(q0.z, q0.w), a_xy, t0), hx0, hy0);
+                            upk2(ffma2(pk2(-q1.z, -q1.w), a_xy, t1), lx1, ly1); upk2(ffma2(pk2(q1.z, q1.w), a_xy, t1), hx1, hy1);
+                            upk2(ffma2(pk2(-q2.z, -q2.w), a_xy, t2), lx2, ly2); upk2(ffma2(pk2(q2.z, q2.w), a_xy, t2), hx2, hy2);
+                            upk2(ffma2(pk2(-q3.z, -q3.w), a_xy, t3), lx3, ly3); upk2(ffma2(pk2(q3.z, q3.w), a_xy, t3), hx3, hy3);
+                            upk2(ffma2(pk2(-q4.z, -q4.w), a_zz, tz01), lz0, lz1); upk2(ffma2(pk2(q4.z, q4.w), a_zz, tz01), hz0, hz1);
+                            upk2(ffma2(pk2(-q5.z, -q5.w), a_zz, tz23), lz2, lz3); upk2(ffma2(pk2(q5.z, q5.w), a_zz, tz23), hz2, hz3);
+                            const float e0 = fmaxf(fmaxf(lx0, ly0), fmaxf(lz0, 0.0f)), x0 = fminf(fminf(hx0, hy0), fminf(hz0, closest.t));
+                            const float e1 = fmaxf(fmaxf(lx1, ly1), fmaxf(lz1, 0.0f)), x1 = fminf(fminf(hx1, hy1), fminf(hz1, closest.t));
+                            const float e2 = fmaxf(fmaxf(lx2, ly2), fmaxf(lz2, 0.0f)), x2 = fminf(fminf(hx2, hy2), fminf(hz2, closest.t));
+                            const float e3 = fmaxf(fmaxf(lx3, ly3), fmaxf(lz3, 0.0f)), x3 = fminf(fminf(hx3, hy3), fminf(hz3, closest.t));
+                            uint32_t k0 = e0 <= x0 ? ((__float_as_uint(e0) & ~S4_REF_MASK) | __float_as_uint(rr.x)) : 0xffffffffu;
+                            uint32_t k1 = e1 <= x1 ? ((__float_as_uint(e1) & ~S4_REF_MASK) | __float_as_uint(rr.y)) : 0xffffffffu;
+                            uint32_t k2 = e2 <= x2 ? ((__float_as_uint(e2) & ~S4_REF_MASK) | __float_as_uint(rr.z)) : 0xffffffffu;
+                            uint32_t k3 = e3 <= x3 ? ((__float_as_uint(e3) & ~S4_REF_MASK) | __float_as_uint(rr.w)) : 0xffffffffu;
                             k0 = sort4_park(k0, k1, k2, k3, sp_addr, STACK_STRIDE);
-                            c = k0 != 0xffffffffu ? (k0 & S4_REF_MASK) : NONE;
+                            c = k0 & S4_REF_MASK;   // 0xffffffff (nothing entered) decodes to NONE
                         } else if constexpr (W4) {
                             // four children: key = 11 bits of entry distance | 21 bits of ref, 0xffffffff = not entered
                             uint4 qa, qb, qc, qd;
@@ -509,7 +558,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                           }
                         }
                     }
-                    if (Q16 ? (c & Q16_LEAF) != 0u : (S4 ? (c & S4_LEAF) != 0u : (int)c < 0)) {   // leaf: park it, or wait for the batch test
+                    if (Q16 ? (c & Q16_LEAF) != 0u : (S4 ? (c >= S4_LEAF && c != S4_NONE) : (int)c < 0)) {   // leaf: park it, or wait for the batch test
                         if (pending == NONE) { pending = c; c = NONE; }
                         else blocked = true;
                     }

@@ -219,9 +219,14 @@ __global__ void build_nodes4_q16_kernel(const RawNode* __restrict__ nodes, uint3
     }
 }
 
-// pass 4d: 4-wide fp32 records for scenes staged in shared memory (megakernel_v3.cu MODE 4): 112 bytes per inner
+// pass 4d: 4-wide fp32 records for scenes staged in shared memory (megakernel_v3.cu MODE 4/5): 112 bytes per inner
 // node = four child boxes as (centre, half extent) + four refs in 11-bit form (bit 10 = leaf, bits 0-9 = inner
-// record / only model of the leaf; 0x800 = empty slot, whose negative half extent is never entered).
+// record / only model of the leaf; 0x7ff = empty slot, whose negative half extent is never entered).
+// The floats are ordered for the packed FFMA2 slab test (two fp32 FMAs per instruction, sm_100):
+//   q[i] = (c_i.x, c_i.y, h_i.x, h_i.y)  i = 0..3      one box, axes x and y side by side
+//   q[4] = (c_0.z, c_1.z, h_0.z, h_1.z)                axis z of boxes 0 and 1 side by side
+//   q[5] = (c_2.z, c_3.z, h_2.z, h_3.z)
+//   q[6] = refs
 __global__ void build_nodes4_ch_kernel(const RawNode* __restrict__ nodes, uint32_t n,
                                        const uint32_t* __restrict__ inner_id, const float4* __restrict__ pairs_ch,
                                        float4* __restrict__ nodes4) {
@@ -230,7 +235,7 @@ __global__ void build_nodes4_ch_kernel(const RawNode* __restrict__ nodes, uint32
     const RawNode nd = nodes[i];
     if (nd.model_count != 0u) return;
     const uint32_t id = inner_id[i];
-    float box[4][6];
+    float box[4][6];   // (c.xyz, h.xyz)
     uint32_t ref[4];
     auto take = [&](int slot, uint32_t rec, uint32_t which) {   // child `which` of pair record `rec`
         const float4 q0 = pairs_ch[4u * rec], q1 = pairs_ch[4u * rec + 1u], q2 = pairs_ch[4u * rec + 2u], q3 = pairs_ch[4u * rec + 3u];
@@ -245,16 +250,17 @@ __global__ void build_nodes4_ch_kernel(const RawNode* __restrict__ nodes, uint32
         if (nodes[x].model_count > 0u) {
             take(2 * s, id, s);
             for (int k = 0; k < 3; k++) { box[2 * s + 1][k] = 0.0f; box[2 * s + 1][3 + k] = -1.0f; }
-            ref[2 * s + 1] = 0x800u;
+            ref[2 * s + 1] = 0x7ffu;
         } else {
             take(2 * s, inner_id[x], 0u);
             take(2 * s + 1, inner_id[x], 1u);
         }
     }
     float4* out = nodes4 + 7u * id;
-    const float* b = &box[0][0];
 #pragma unroll
-    for (int k = 0; k < 6; k++) out[k] = make_float4(b[4 * k], b[4 * k + 1], b[4 * k + 2], b[4 * k + 3]);
+    for (int k = 0; k < 4; k++) out[k] = make_float4(box[k][0], box[k][1], box[k][3], box[k][4]);
+    out[4] = make_float4(box[0][2], box[1][2], box[0][5], box[1][5]);
+    out[5] = make_float4(box[2][2], box[3][2], box[2][5], box[3][5]);
     out[6] = make_float4(__uint_as_float(ref[0]), __uint_as_float(ref[1]), __uint_as_float(ref[2]), __uint_as_float(ref[3]));
 }
 

@@ -13,6 +13,22 @@ __global__ void axpby_kernel(float* __restrict__ dst, float dw, const float* __r
         dst[i] = __fadd_rn(__fmul_rn(dst[i], dw), __fmul_rn(src[i], sw));
 }
 
+// in-place scale (dst and src of axpby must not alias: both are __restrict__)
+__global__ void scale_kernel(float* __restrict__ dst, float w, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __fmul_rn(dst[i], w);
+}
+
+// fragment's depth composite (raytrace.wgsl:104-120) as a pass of its own: used when the ray-traced colour and depth
+// of one frame are the sum of several ranks' partial frames and can only be compared with the raster depth afterwards
+__global__ void composite_kernel(float4* __restrict__ rgba, const float* __restrict__ rt_depth,
+                                 const float4* __restrict__ raster_rgba, const float* __restrict__ raster_depth,
+                                 CameraParams cam, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (raster_wins(cam, raster_depth[i], rt_depth[i])) rgba[i] = raster_rgba[i];
+}
+
 // gathered: shard_count planes, each `shard_stride_words` words, shard-local rows of width*channels words
 __global__ void unshard_kernel(const uint32_t* __restrict__ gathered, size_t shard_stride_words,
                                uint32_t* __restrict__ full, uint32_t width, uint32_t height, uint32_t channels,
@@ -36,7 +52,18 @@ int launch_axpby(float* dst, float dw, const float* src, float sw, size_t n, cud
     if (n == 0) return 0;
     const int block = 256;
     const int grid = (int)((n + block - 1) / block < 148 * 8 ? (n + block - 1) / block : 148 * 8);
-    axpby_kernel<<<grid, block, 0, stream>>>(dst, dw, src, sw, n);
+    // a zero source weight (or src == dst) is a plain scale: src is not read, so an Inf there cannot turn into NaN
+    if (sw == 0.0f || src == dst || src == nullptr) scale_kernel<<<grid, block, 0, stream>>>(dst, src == dst ? dw + sw : dw, n);
+    else axpby_kernel<<<grid, block, 0, stream>>>(dst, dw, src, sw, n);
+    return 1;
+}
+
+int launch_composite(float4* rgba, const float* rt_depth, const float4* raster_rgba, const float* raster_depth,
+                     const CameraParams& cam, size_t n, cudaStream_t stream) {
+    if (n == 0) return 0;
+    const int block = 256;
+    const int grid = (int)((n + block - 1) / block < 148 * 8 ? (n + block - 1) / block : 148 * 8);
+    composite_kernel<<<grid, block, 0, stream>>>(rgba, rt_depth, raster_rgba, raster_depth, cam, n);
     return 1;
 }
 

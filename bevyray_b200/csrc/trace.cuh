@@ -24,7 +24,8 @@ namespace bvr {
 #define BVR_LEAF_FIRST_MASK 0x00ffffffu
 #define BVR_MAX_LEAF_COUNT 128u
 #define BVR_REF_STACK 32   // raytrace.wgsl:310 STACKSIZE
-#define BVR_FAST_STACK 64
+#define BVR_FAST_STACK 128  // near-first stack of the fallback kernel: one entry per tree level (an LBVH over 63-bit
+                            // keys plus index tie-break has at most 64 + log2(n) levels)
 
 struct SceneView {
     const float4* __restrict__ pairs;            // 4 x float4 per inner node: child boxes as (min, max)

@@ -4,9 +4,11 @@ Two shardings:
   * "tiles"   — interleaved row strips; every rank renders its strips for all samples with the
                 reference's per-pixel RNG stream, so the gathered image is bit-identical to 1 GPU.
                 Exchange: all_gather of equal-size shard planes + one de-interleave kernel.
-  * "samples" — rank g renders `sample_count` samples of the whole frame with its own random_seed
-                (what the reference does across frames, extract.rs:72-73); the per-rank averages are
-                summed with an NCCL reduce to rank 0 and scaled by 1/world.
+  * "samples" — rank g renders its share of the samples of the whole frame with its own random_seed (what the
+                reference does across frames, extract.rs:72-73): spp_g = split_samples(spp, world)[g].  Every rank
+                scales its partial average by spp_g / spp, the weighted partials (colour and, for levels 1-2, the
+                ray-traced depth) are summed with an NCCL reduce to rank 0, and the depth composite with the raster
+                output runs once, on the sum (bvr_composite_device).
 torch is plumbing only (device memory, streams, NCCL); every kernel on the render path is in
 libbevyray_b200.so."""
 import numpy as np
@@ -26,6 +28,11 @@ def shard_global_rows(height, shard_index, shard_count, strip_rows):
         return np.arange(height)
     ly = np.arange(rows)
     return ((ly // strip_rows) * shard_count + shard_index) * strip_rows + (ly % strip_rows)
+
+
+def split_samples(spp, world):
+    """Samples per rank when `spp` samples are shared out: the first spp % world ranks get one more."""
+    return [spp // world + (1 if g < spp % world else 0) for g in range(world)]
 
 
 def seed_for_rank(base_seed, rank, world, mode):
@@ -67,28 +74,57 @@ class ShardedRenderer:
         return make_options(width, kernel, traversal)
 
     def render_frame(self, camera, level, base_seed, width, height, kernel=capi.KERNEL_AUTO,
-                     traversal=capi.TRAVERSAL_AUTO, d_raster_rgba=0, d_raster_depth=0):
+                     traversal=capi.TRAVERSAL_AUTO, d_raster_rgba=0, d_raster_depth=0, split_samples_of=None):
         """Enqueues one frame on the current stream.  Returns the device tensor that holds the full
-        fp32 RGBA frame on rank 0 (on every rank for "tiles")."""
+        fp32 RGBA frame on rank 0 (on every rank for "tiles").
+
+        "samples" mode: `camera.sample_count` samples are rendered by THIS rank; with split_samples_of = S the
+        frame is the S-sample frame shared out over the ranks (camera.sample_count is overridden by this rank's share,
+        and the partial frames are weighted by their share).  Without it every rank contributes sample_count samples
+        with equal weight."""
         opts = self.options(width, kernel, traversal)
         win = make_window(self.seed_for_rank(base_seed), height)
         lv = make_level(level)
         rows = self.ctx.shard_rows(height, opts)
         shard = self._buf("shard", (rows, width, 4), torch.float32)
-        self.ctx.render_device(camera, lv, win, opts, d_raster_rgba, d_raster_depth, rgba=shard.data_ptr())
-        if self.world == 1:
-            return shard
-        if self.mode == "samples":
-            dist.reduce(shard, dst=0, op=dist.ReduceOp.SUM)
+        if self.world == 1 or self.mode == "tiles":
+            self.ctx.render_device(camera, lv, win, opts, d_raster_rgba, d_raster_depth, rgba=shard.data_ptr())
+            if self.world == 1:
+                return shard
+            gathered = self._buf("gathered", (self.world, rows, width, 4), torch.float32)
+            dist.all_gather_into_tensor(gathered, shard)
+            full = self._buf("full", (height, width, 4), torch.float32)
+            self.ctx.unshard_device(gathered.data_ptr(), rows * width * 4, full.data_ptr(), width, height, 4,
+                                    self.world, self.strip_rows)
+            return full
+        # ---- samples ----
+        cam = camera
+        weight = 1.0 / self.world
+        if split_samples_of is not None:
+            share = split_samples(int(split_samples_of), self.world)[self.rank]
+            cam = type(camera).from_buffer_copy(camera)
+            cam.sample_count = share
+            weight = share / float(split_samples_of)
+        composite = int(level) in (1, 2)
+        depth = self._buf("depth", (rows, width), torch.float32) if composite else None
+        if cam.sample_count == 0:
+            shard.zero_()                    # more ranks than samples: this rank contributes nothing
+            if composite:
+                depth.zero_()
+        else:
+            opts.flags |= capi.RENDER_DEFER_COMPOSITE
+            self.ctx.render_device(cam, lv, win, opts, 0, 0, rgba=shard.data_ptr(),
+                                   **({"rt_depth": depth.data_ptr()} if composite else {}))
+            self.ctx.axpby_device(shard.data_ptr(), weight, 0, 0.0, shard.numel())       # in-place scale
+            if composite:
+                self.ctx.axpby_device(depth.data_ptr(), weight, 0, 0.0, depth.numel())
+        dist.reduce(shard, dst=0, op=dist.ReduceOp.SUM)
+        if composite:
+            dist.reduce(depth, dst=0, op=dist.ReduceOp.SUM)
             if self.rank == 0:
-                self.ctx.axpby_device(shard.data_ptr(), 1.0 / self.world, shard.data_ptr(), 0.0, shard.numel())
-            return shard
-        gathered = self._buf("gathered", (self.world, rows, width, 4), torch.float32)
-        dist.all_gather_into_tensor(gathered, shard)
-        full = self._buf("full", (height, width, 4), torch.float32)
-        self.ctx.unshard_device(gathered.data_ptr(), rows * width * 4, full.data_ptr(), width, height, 4,
-                                self.world, self.strip_rows)
-        return full
+                self.ctx.composite_device(camera, lv, shard.data_ptr(), depth.data_ptr(), d_raster_rgba, d_raster_depth,
+                                          rows * width)
+        return shard
 
     def close(self):
         self.ctx.close()

@@ -163,8 +163,16 @@ typedef struct BvrRenderOptions {
     uint32_t shard_index;
     uint32_t shard_count;
     uint32_t strip_rows;   /* 0 = default (8) */
-    uint32_t reserved[2];
+    uint32_t flags;        /* BvrRenderFlags */
+    uint32_t reserved;
 } BvrRenderOptions;
+
+typedef enum BvrRenderFlags {
+    /* Levels 1-2: skip the depth composite (raytrace.wgsl:104-120) but keep the level's fallback depth for misses
+     * (raytrace.wgsl:177-182).  For sample sharding: the partial frames of all ranks are summed first (colour AND
+     * rt_depth), then bvr_composite_device compares the summed depth with the raster depth once. */
+    BVR_RENDER_DEFER_COMPOSITE = 1u
+} BvrRenderFlags;
 
 /* Output planes.  Any pointer may be NULL (plane not produced / not copied).
  * For a sharded render each plane holds only this shard's rows, strips concatenated in order:
@@ -207,6 +215,10 @@ const char* bvr_last_error(const BvrContext* ctx);
 /* Run all work of this context on `cuda_stream` (a cudaStream_t; NULL = the context's own stream). */
 int bvr_set_stream(BvrContext* ctx, void* cuda_stream);
 int bvr_sync(BvrContext* ctx);
+
+/* Experiment knobs (BVR_NO_TIGHT, BVR_NO_BVH4, BVR_MK_THREADS, ...) are read from the environment once,
+ * in bvr_create; this re-reads them for an existing context (A/B tests).  Production never calls it. */
+int bvr_reload_tuning(BvrContext* ctx);
 
 /* Upload the scene in the reference's layout.  `ranges == NULL` uploads everything; otherwise only
  * the listed element ranges are copied (pinned staging -> HBM) and the device-side traversal layout
@@ -261,9 +273,16 @@ int bvr_render_device(BvrContext* ctx,
                       const BvrOutputs* device_out);
 
 /* Sample sharding: dst[i] = (dst[i]*dst_weight + src[i]*src_weight) on device;
- * used to combine per-seed partial averages after an NCCL reduce.  n = number of floats. */
+ * used to weight per-seed partial averages around an NCCL reduce.  n = number of floats.  src_weight == 0 (or
+ * d_src == d_dst) is an in-place scale: d_src is not read. */
 int bvr_axpby_device(BvrContext* ctx, float* d_dst, float dst_weight,
                      const float* d_src, float src_weight, size_t n);
+
+/* The depth composite of `fragment` (raytrace.wgsl:104-120) as a pass of its own, for frames rendered with
+ * BVR_RENDER_DEFER_COMPOSITE: rgba[i] = raster_rgba[i] where the raster depth wins against rt_depth[i].  Levels 0 and 3
+ * have no depth test: no-op.  All pointers are device pointers; n_pixels texels. */
+int bvr_composite_device(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level, float* d_rgba,
+                         const float* d_rt_depth, const float* d_raster_rgba, const float* d_raster_depth, size_t n_pixels);
 
 /* Tile sharding: scatter `shard_count` gathered shard planes (each bvr_shard_rows()-max rows of
  * `width` pixels x `channels` 32-bit words, laid out back to back with `shard_stride_words`)
@@ -277,6 +296,9 @@ int bvr_get_stats(BvrContext* ctx, BvrStats* out);
 /* Measurement helper (not on the render path): FP32 FMA throughput of `device` in TFLOP/s, the
  * denominator of the FP32 roofline (MEASURED_PEAKS.json has no FP32 figure). */
 int bvr_bench_fp32_peak(int device, float* tflops_out);
+/* Measurement helper: L2 -> SM read bandwidth of `device` in GB/s (a 32 MiB L2-resident buffer streamed by every
+ * CTA): the roofline denominator for scenes whose nodes are fetched from L2 (BASELINE configs[3]). */
+int bvr_bench_l2_bandwidth(int device, float* gbs_out);
 
 #ifdef __cplusplus
 } /* extern "C" */

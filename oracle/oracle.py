@@ -20,6 +20,47 @@ if not os.path.exists(_LIB):
 lib = C.CDLL(_LIB)
 
 
+# The uniforms `fragment` reads, as the reference's encase layouts (extract.rs:56-61, 83-104; raytrace.wgsl:30-54).  The
+# oracle's own mirrors: a caller may pass these or any other object with the same bytes (the product's ctypes structs).
+class Camera(C.Structure):
+    _fields_ = [("sample_count", C.c_uint32), ("bounce_count", C.c_uint32), ("projection", C.c_uint32),
+                ("near_plane", C.c_float), ("far_plane", C.c_float), ("fov", C.c_float), ("aspect", C.c_float),
+                ("_pad0", C.c_uint32), ("position", C.c_float * 3), ("_pad1", C.c_uint32),
+                ("direction", C.c_float * 3), ("_pad2", C.c_uint32), ("up", C.c_float * 3), ("_pad3", C.c_uint32)]
+
+
+class RaytraceLevel(C.Structure):
+    _fields_ = [("level", C.c_uint32), ("_pad0", C.c_uint32 * 3), ("_padding", C.c_float * 3), ("_pad1", C.c_uint32)]
+
+
+class Window(C.Structure):
+    _fields_ = [("random_seed", C.c_float), ("height", C.c_uint32), ("_padding", C.c_float * 2)]
+
+
+assert C.sizeof(Camera) == 80 and C.sizeof(RaytraceLevel) == 32 and C.sizeof(Window) == 16
+
+MODEL_DTYPE = np.dtype({"names": ["position", "radius", "material_id"], "formats": [("<f4", 3), "<f4", "<u4"],
+                        "offsets": [0, 12, 16], "itemsize": 32})
+MATERIAL_DTYPE = np.dtype({"names": ["base_color", "metallic", "roughness", "reflectance", "ior", "specular_transmission"],
+                           "formats": [("<f4", 3), "<f4", "<f4", "<f4", "<f4", "<f4"], "offsets": [0, 12, 16, 20, 24, 28],
+                           "itemsize": 32})
+BVH_NODE_DTYPE = np.dtype({"names": ["bounds_min", "bounds_max", "index", "model_count"],
+                           "formats": [("<f4", 3), ("<f4", 3), "<u4", "<u4"], "offsets": [0, 16, 28, 32], "itemsize": 48})
+
+
+def make_level(level):
+    lv = RaytraceLevel()
+    lv.level = int(level)
+    return lv
+
+
+def make_window(random_seed, height):
+    w = Window()
+    w.random_seed = float(random_seed)
+    w.height = int(height)
+    return w
+
+
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "paths", "node_pops", "inner_visits", "box_tests", "sphere_tests",
                                           "hits_shaded", "rng_draws", "stack_truncations", "max_stack")]

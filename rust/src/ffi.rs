@@ -61,7 +61,8 @@ pub struct BvrRenderOptions {
     pub shard_index: u32,
     pub shard_count: u32,
     pub strip_rows: u32,
-    pub reserved: [u32; 2],
+    pub flags: u32,
+    pub reserved: u32,
 }
 
 #[repr(C)]

@@ -308,6 +308,57 @@ def test_deep_tree_falls_back_to_reference_order(bvr, oracle, ctx):
     check(got, want)
 
 
+def test_uploaded_trees_of_32_to_63_levels_truncate_like_the_reference(bvr, oracle, ctx):
+    """raytrace.wgsl:320 abandons a traversal once its stack index reaches 32, which a tree of 32+ levels can trigger.
+    For an uploaded tree that deep the library runs the verbatim reference-order kernel: here a 40-level
+    tree of overlapping spheres whose layout leaves one stack entry behind per level, so the oracle does truncate."""
+    n = 40
+    rs = np.random.RandomState(4)
+    models = np.zeros(n, bvr.MODEL_DTYPE)
+    # all spheres on one line of sight, overlapping boxes: a ray down the line enters every box
+    models["position"][:, 0] = rs.uniform(-0.3, 0.3, n)
+    models["position"][:, 1] = rs.uniform(-0.3, 0.3, n)
+    models["position"][:, 2] = -8 - 0.8 * np.arange(n)
+    models["radius"] = 0.5
+    models["material_id"] = np.arange(n) % 2
+    mats = np.zeros(2, bvr.MATERIAL_DTYPE)
+    mats["base_color"] = [(0.8, 0.6, 0.2), (0.3, 0.6, 0.9)]
+    mats["roughness"] = 0.5
+    mats["ior"] = 1.5
+    pad = models["radius"] + np.float32(0.1)
+    lo, hi = models["position"] - pad[:, None], models["position"] + pad[:, None]
+    # node layout: inner k at index 2k (k = 0..n-2), children at 2k+1 (LEAF k) and 2k+2 (the rest: inner k+1 or the
+    # last leaf).  The reference pushes 2k+1 first and 2k+2 second, pops the REST first: the leaves pile up on its stack,
+    # one per level -> the stack index reaches 32 at level 31 and the traversal is abandoned.
+    nodes = np.zeros(2 * n - 1, bvr.BVH_NODE_DTYPE)
+    for k in range(n - 1):
+        nodes["index"][2 * k], nodes["model_count"][2 * k] = 2 * k + 1, 0
+        nodes["bounds_min"][2 * k], nodes["bounds_max"][2 * k] = lo[k:].min(axis=0), hi[k:].max(axis=0)
+        nodes["index"][2 * k + 1], nodes["model_count"][2 * k + 1] = k, 1
+        nodes["bounds_min"][2 * k + 1], nodes["bounds_max"][2 * k + 1] = lo[k], hi[k]
+    nodes["index"][-1], nodes["model_count"][-1] = n - 1, 1
+    nodes["bounds_min"][-1], nodes["bounds_max"][-1] = lo[-1], hi[-1]
+    assert bvr.validate_bvh(nodes, models) is None
+    ranks, depth = bvr.traversal_ranks(nodes, n)
+    assert 32 <= depth == n < 64
+    W, H = 64, 48
+    cam = bvr.make_camera(position=(0, 0, 0), target=(0, 0, -1), fov=0.3, aspect=W / H, sample_count=2, bounces=3)
+    win = bvr.make_window(0.3, H)
+    ctx.upload_scene(models, mats, nodes)
+    got = ctx.render(cam, 3, win, bvr.make_options(W))
+    want, cnt = oracle.render(models, mats, nodes, cam, bvr.make_level(3), win, W)
+    assert cnt["stack_truncations"] > 0                      # the case is real: the reference does give up here
+    check(got, want)
+    assert ctx.stats()["rays"] == cnt["rays"]
+    # the same spheres with a tree built by the library (bvr_upload_scene_gpu_bvh) are walked completely: the closest
+    # hit of every camera ray equals brute force over all spheres
+    ctx.upload_scene_gpu_bvh(models, mats)
+    got2 = ctx.render(cam, 3, win, bvr.make_options(W))
+    brute, _ = oracle.render(models, mats, nodes, cam, bvr.make_level(3), win, W, brute_force=True)
+    assert np.array_equal(got2["primary_id"], brute["primary_id"]) and np.array_equal(bits(got2["primary_depth"]), bits(brute["primary_depth"]))
+    assert not np.array_equal(want["primary_id"], brute["primary_id"])   # truncation changed what the reference sees
+
+
 def test_app_mirror_renders_demo_scene(bvr, oracle):
     """RaytracePlugin + one frame of the schedule (extract -> prepare_buffers -> RayTracingNode::run),
     src/raytracing/{mod,extract,pipeline}.rs, at the demo defaults (FallbackRaytraced, 4 spp, 4 bounces)."""

@@ -114,6 +114,7 @@ def test_c4_size_full_frame_against_oracle(bvr, oracle, ctx):
             for k in ("BVR_NO_BVH4", "BVR_NO_Q16"):
                 os.environ.pop(k, None)
             os.environ.update(env)
+            ctx.reload_tuning()
             if "BVR_NO_Q16" in env:
                 ctx.upload_scene(scene.models, scene.materials, scene.nodes)   # the records are chosen at upload
             got = ctx.render(cam, 3, win, bvr.make_options(W, traversal=traversal))
@@ -123,3 +124,4 @@ def test_c4_size_full_frame_against_oracle(bvr, oracle, ctx):
     finally:
         for k in ("BVR_NO_BVH4", "BVR_NO_Q16"):
             os.environ.pop(k, None)
+        ctx.reload_tuning()

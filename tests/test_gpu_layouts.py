@@ -1,7 +1,7 @@
 """Every node layout / kernel variant of the megakernel against the oracle (bit-exact).  The variants are picked by
 the library from the scene; the environment knobs below force the others for A/B runs:
   small scenes (staged in shared memory): 4-wide fp32 records (default), child-pair records (BVR_NO_BVH4),
-      two paths per lane (BVR_MK_VARIANT=4), warp-specialised ray pool (BVR_MK_VARIANT=5), one thread per pixel (BVR_MK_V1);
+      one thread per pixel (BVR_MK_V1);
   big scenes (walked in HBM/L2): 4-wide 16-bit records (default), 2-wide 16-bit records (BVR_NO_BVH4),
       fp32 child-pair records (BVR_NO_Q16, chosen at upload)."""
 import os
@@ -11,7 +11,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-KNOBS = ("BVR_NO_BVH4", "BVR_NO_Q16", "BVR_NO_TIGHT", "BVR_MK_VARIANT", "BVR_MK_V1", "BVR_MK_THREADS", "BVR_GPU_VALIDATE")
+KNOBS = ("BVR_NO_BVH4", "BVR_NO_Q16", "BVR_NO_TIGHT", "BVR_MK_V1", "BVR_MK_THREADS", "BVR_GPU_VALIDATE", "BVR_NO_TOP")
 
 
 def bits(a):
@@ -19,18 +19,21 @@ def bits(a):
 
 
 @pytest.fixture
-def knobs():
+def knobs(ctx):
+    """The library reads its experiment knobs once per context (bvr_create); bvr_reload_tuning re-reads them."""
     saved = {k: os.environ.pop(k, None) for k in KNOBS}
 
     def set_(**kw):
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update({k: str(v) for k, v in kw.items()})
+        ctx.reload_tuning()
     yield set_
     for k in KNOBS:
         os.environ.pop(k, None)
         if saved[k] is not None:
             os.environ[k] = saved[k]
+    ctx.reload_tuning()
 
 
 def check(got, want, cnt, stats, tag):
@@ -39,7 +42,7 @@ def check(got, want, cnt, stats, tag):
     assert stats["rays"] == cnt["rays"], tag
 
 
-SMALL = [dict(), dict(BVR_NO_BVH4=1), dict(BVR_MK_VARIANT=4), dict(BVR_MK_VARIANT=5), dict(BVR_MK_V1=1),
+SMALL = [dict(), dict(BVR_NO_BVH4=1), dict(BVR_NO_TIGHT=1), dict(BVR_MK_V1=1),
          dict(BVR_MK_THREADS=512), dict(BVR_NO_BVH4=1, BVR_MK_THREADS=768)]
 
 
@@ -99,7 +102,7 @@ def test_quantised_records_refuse_boxes_outside_the_root(bvr, oracle, ctx, knobs
 
 
 @pytest.mark.parametrize("gpu_bvh", [False, True], ids=["host-ploc", "gpu-lbvh"])
-@pytest.mark.parametrize("env", [dict(), dict(BVR_NO_TIGHT=1), dict(BVR_NO_BVH4=1), dict(BVR_MK_VARIANT=4), dict(BVR_MK_VARIANT=5),
+@pytest.mark.parametrize("env", [dict(), dict(BVR_NO_TIGHT=1), dict(BVR_NO_BVH4=1),
                                  dict(BVR_MK_V1=1), dict(BVR_GPU_VALIDATE=1)],
                          ids=lambda e: "-".join(f"{k[4:]}={v}" for k, v in e.items()) or "default")
 def test_exact_ties_go_to_the_sphere_the_reference_reaches_first(bvr, oracle, ctx, knobs, env, gpu_bvh):
@@ -162,6 +165,10 @@ def test_gpu_side_validation_rejects_what_the_host_walk_rejects(bvr, rtiow, knob
         bad["index"][inner[3]] = len(bad) - 1; cases.append(bad)                               # second child out of range
         bad = rtiow.nodes.copy(); bad["index"][inner[5]] = bad["index"][inner[7]]; cases.append(bad)   # two parents
         bad = rtiow.nodes.copy(); bad["model_count"][leaf] = 200; cases.append(bad)           # leaf too large
+        # a node the root does not reach, with a child index far outside the array (the derive kernels visit it too)
+        bad = np.zeros(len(rtiow.nodes) + 1, bvr.BVH_NODE_DTYPE); bad[:-1] = rtiow.nodes
+        bad["index"][-1], bad["model_count"][-1] = 0x7ffffff0, 0; cases.append(bad)
+        bad = bad.copy(); bad["index"][-1], bad["model_count"][-1] = len(rtiow.models) + 9, 1; cases.append(bad)
         for k, nodes in enumerate(cases):
             with pytest.raises(bvr.BvrError) as e:
                 c.upload_scene(rtiow.models, rtiow.materials, nodes)

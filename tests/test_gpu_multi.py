@@ -9,6 +9,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 W, H = 256, 144
+SPP_TOTAL = 5          # samples mode: shared out as 3 + 2
+
+
+def _raster():
+    rs = np.random.RandomState(5)
+    return rs.rand(H, W, 4).astype(np.float32), (rs.rand(H, W) * 0.06).astype(np.float32)
 
 
 def _free_port():
@@ -32,7 +38,14 @@ def _worker(rank, world, port, mode, out_dir):
     cam = bvr.make_camera(sample_count=4, bounces=6, aspect=W / H)
     r = ShardedRenderer(rank, rank, world, mode=mode, strip_rows=4)
     r.upload_scene(scene.models, scene.materials, scene.nodes)
-    frame = r.render_frame(cam, 3, 0.37, W, H)
+    if mode == "tiles":
+        frame = r.render_frame(cam, 3, 0.37, W, H)
+    else:
+        # level 2: weighted partial frames, colour and depth reduced, composite once on rank 0
+        rc, rd = _raster()
+        d_rc, d_rd = torch.from_numpy(rc).cuda(), torch.from_numpy(rd).cuda()
+        frame = r.render_frame(cam, 2, 0.37, W, H, d_raster_rgba=d_rc.data_ptr(), d_raster_depth=d_rd.data_ptr(),
+                               split_samples_of=SPP_TOTAL)
     torch.cuda.synchronize()
     if rank == 0:
         np.save(os.path.join(out_dir, mode + ".npy"), frame.cpu().numpy())
@@ -57,8 +70,21 @@ def test_two_gpu_sharding(tmp_path, bvr, mode):
         want = ctx.render(cam, 3, bvr.make_window(0.37, H), bvr.make_options(W), want=("rgba",))["rgba"]
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     else:
+        from bevyray_b200.distributed import split_samples
         acc = np.zeros((H, W, 4), np.float32)
-        for r in range(2):
-            acc += ctx.render(cam, 3, bvr.make_window(seed_for_rank(0.37, r, 2, "samples"), H), bvr.make_options(W), want=("rgba",))["rgba"]
-        assert np.array_equal(got, acc * np.float32(0.5))
+        dep = np.zeros((H, W), np.float32)
+        for r, share in enumerate(split_samples(SPP_TOTAL, 2)):
+            c = bvr.make_camera(sample_count=share, bounces=6, aspect=W / H)
+            p = ctx.render(c, 3, bvr.make_window(seed_for_rank(0.37, r, 2, "samples"), H), bvr.make_options(W), want=("rgba", "rt_depth"))
+            wgt = np.float32(share / float(SPP_TOTAL))
+            acc += p["rgba"] * wgt
+            dep += p["rt_depth"] * wgt
+        rc, rd = _raster()
+        with np.errstate(divide="ignore"):
+            d = np.where(dep > np.float32(cam.far_plane), np.float32(-1.0), np.float32(cam.near_plane) / dep)
+        want = acc.copy()
+        want[rd > d] = rc[rd > d]
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        from_raster = (got == rc).all(axis=2)
+        assert 0 < from_raster.sum() < from_raster.size
     ctx.close()

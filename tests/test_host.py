@@ -182,3 +182,30 @@ def test_traversal_ranks_follow_the_reference_order(bvr):
     with pytest.raises(bvr.BvrError) as e:
         bvr.traversal_ranks(nodes, 7)
     assert e.value.status == bvr.capi.BVR_ERR_BAD_SCENE
+
+
+def test_unreachable_nodes_are_validated_too(bvr, rtiow):
+    """The derive kernels run over EVERY node of the array, so a node the root does not reach must still be in range
+    (and the GPU validator, scene_validate.cu: gv_link, checks every node as well): same verdict on both paths."""
+    n = len(rtiow.nodes)
+    for mutate in ("child", "leaf", "leaf_count", "second_parent"):
+        nodes = np.zeros(n + 3, bvr.BVH_NODE_DTYPE)
+        nodes[:n] = rtiow.nodes
+        # three extra nodes the root never reaches: one inner node with two leaf children — valid on their own
+        nodes["index"][n], nodes["model_count"][n] = n + 1, 0
+        nodes["index"][n + 1], nodes["model_count"][n + 1] = 0, 1
+        nodes["index"][n + 2], nodes["model_count"][n + 2] = 1, 1
+        ranks, depth = bvr.traversal_ranks(nodes, len(rtiow.models))
+        want, want_depth = bvr.traversal_ranks(rtiow.nodes, len(rtiow.models))
+        assert np.array_equal(ranks, want) and depth == want_depth
+        if mutate == "child":
+            nodes["index"][n] = 0x7ffffff0                      # child far outside the array
+        elif mutate == "leaf":
+            nodes["index"][n + 1] = len(rtiow.models) + 5        # model range outside the model buffer
+        elif mutate == "leaf_count":
+            nodes["model_count"][n + 2] = 129
+        else:
+            nodes["index"][n] = int(rtiow.nodes["index"][0])     # claims the root's children: two parents
+        with pytest.raises(bvr.BvrError) as e:
+            bvr.traversal_ranks(nodes, len(rtiow.models))
+        assert e.value.status == bvr.capi.BVR_ERR_BAD_SCENE, mutate

@@ -12,6 +12,23 @@ import torch.multiprocessing as mp
 
 W, H, STRIP = 96, 54, 4
 BASE_SEED = 0.37
+SPP_TOTAL = 3          # shared out over two ranks as 2 + 1 (weights 2/3 and 1/3)
+
+
+def _raster(h, w):
+    """Synthetic raster colour / reverse-Z depth for the level-2 composite."""
+    rs = np.random.RandomState(5)
+    return rs.rand(h, w, 4).astype(np.float32), (rs.rand(h, w) * 0.06).astype(np.float32)
+
+
+def _composite(rgba, rt_depth, raster_rgba, raster_depth, near, far):
+    """fragment's depth test (raytrace.wgsl:104-120) in numpy: the raster texel wins where its depth is larger."""
+    with np.errstate(divide="ignore"):
+        d = np.where(rt_depth > np.float32(far), np.float32(-1.0), np.float32(near) / rt_depth)
+    out = rgba.copy()
+    wins = raster_depth > d
+    out[wins] = raster_rgba[wins]
+    return out
 
 
 def _free_port():
@@ -52,12 +69,22 @@ def _worker(rank, world, port, mode, out_dir):
                 full[rr[valid]] = gathered[r].numpy()[valid]
             np.save(os.path.join(out_dir, "tiles.npy"), full)
     else:
+        # level 2 (FallbackRaytraced): the partial frames are weighted by their share of the samples, colour AND
+        # ray-traced depth are summed, and the composite runs once on rank 0 — the steps of ShardedRenderer.render_frame.
+        # Un-composited level 2 == level 3 (same fallback depth for misses, raytrace.wgsl:177-182).
+        from bevyray_b200.distributed import split_samples
+        share = split_samples(SPP_TOTAL, world)[rank]
+        cam_r = bvr.make_camera(sample_count=share, bounces=4, aspect=W / H)
         win = bvr.make_window(seed_for_rank(BASE_SEED, rank, world, mode), H)
-        planes, _ = oracle.render(scene.models, scene.materials, scene.nodes, cam, lvl, win, W, threads=1)
-        t = torch.from_numpy(planes["rgba"].copy())
+        planes, _ = oracle.render(scene.models, scene.materials, scene.nodes, cam_r, lvl, win, W, threads=1)
+        wgt = np.float32(share / float(SPP_TOTAL))
+        t = torch.from_numpy(planes["rgba"] * wgt)
+        d = torch.from_numpy(planes["rt_depth"] * wgt)
         dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+        dist.reduce(d, dst=0, op=dist.ReduceOp.SUM)
         if rank == 0:
-            np.save(os.path.join(out_dir, "samples.npy"), (t.numpy() * np.float32(1.0 / world)))
+            rc, rd = _raster(H, W)
+            np.save(os.path.join(out_dir, "samples.npy"), _composite(t.numpy(), d.numpy(), rc, rd, cam.near_plane, cam.far_plane))
     dist.destroy_process_group()
 
 
@@ -74,15 +101,37 @@ def test_two_rank_sharding(tmp_path, bvr, oracle, mode):
         got = np.load(tmp_path / "tiles.npy")
         assert np.array_equal(got.view(np.uint32), want["rgba"].view(np.uint32))
     else:
-        # sample sharding == the average of one frame per rank seed (what the reference does across frames)
-        acc = np.zeros((H, W, 4), np.float32)
+        # sample sharding == the share-weighted sum of one frame per rank seed, composited once
+        from bevyray_b200.distributed import split_samples
+        shares = split_samples(SPP_TOTAL, world)
+        assert shares == [2, 1]
         seeds = [seed_for_rank(BASE_SEED, r, world, "samples") for r in range(world)]
         assert len(set(seeds)) == world and all(0.0 <= s < 1.0 for s in seeds)
-        for s in seeds:
-            p, _ = oracle.render(scene.models, scene.materials, scene.nodes, cam, bvr.make_level(3), bvr.make_window(s, H), W)
-            acc += p["rgba"]
+        acc = np.zeros((H, W, 4), np.float32)
+        dep = np.zeros((H, W), np.float32)
+        for s_, share in zip(seeds, shares):
+            c = bvr.make_camera(sample_count=share, bounces=4, aspect=W / H)
+            p, _ = oracle.render(scene.models, scene.materials, scene.nodes, c, bvr.make_level(3), bvr.make_window(s_, H), W)
+            wgt = np.float32(share / float(SPP_TOTAL))
+            acc += p["rgba"] * wgt
+            dep += p["rt_depth"] * wgt
+        rc, rd = _raster(H, W)
+        want = _composite(acc, dep, rc, rd, cam.near_plane, cam.far_plane)
         got = np.load(tmp_path / "samples.npy")
-        assert np.array_equal(got, acc * np.float32(0.5))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        # ... and the composite did pick texels from both sources
+        from_raster = (got == rc).all(axis=2)
+        assert 0 < from_raster.sum() < from_raster.size
+
+
+def test_split_samples():
+    from bevyray_b200.distributed import split_samples
+    assert split_samples(100, 8) == [13, 13, 13, 13, 12, 12, 12, 12]
+    assert split_samples(100, 1) == [100]
+    assert split_samples(3, 4) == [1, 1, 1, 0]
+    for spp in (1, 7, 64, 100, 1000):
+        for world in (1, 2, 3, 4, 8):
+            assert sum(split_samples(spp, world)) == spp
 
 
 def test_shard_rows_partition(bvr):

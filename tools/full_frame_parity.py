@@ -13,6 +13,7 @@ ctx = bvr.Context(0)
 for env in ({}, {"BVR_NO_TIGHT": "1"}, {"BVR_NO_BVH4": "1"}, {"BVR_TIGHT_PAD": "200"}, {"BVR_TIGHT_PAD": "400"}):
     for k in ("BVR_NO_TIGHT", "BVR_NO_BVH4", "BVR_TIGHT_PAD"): os.environ.pop(k, None)
     os.environ.update(env)
+    ctx.reload_tuning()
     ctx.upload_scene(scene.models, scene.materials, scene.nodes)
     got = ctx.render(cam, 3, win, bvr.make_options(W)); st = ctx.stats()
     bad = np.zeros((H, W), bool)
