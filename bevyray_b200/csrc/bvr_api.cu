@@ -54,7 +54,7 @@ struct PinnedBuffer {
 // only on request (bvr_reload_tuning); production uses the defaults.
 struct EnvTuning {
     int no_tight = 0, tight_pad = 100, no_q16 = 0, no_bvh4 = 0, gpu_validate = -1, wf_refill = 8;
-    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0;
+    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0, no_both = 0;
 };
 
 struct BvrContext {
@@ -151,6 +151,7 @@ EnvTuning read_env_tuning() {
     t.mk_leaf = env_int("BVR_MK_LEAF", 0);
     t.selfcheck = env_int("BVR_SELFCHECK", 0);
     t.no_top = env_int("BVR_NO_TOP", 0);
+    t.no_both = env_int("BVR_NO_BOTH", 0);
     return t;
 }
 
@@ -803,7 +804,7 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
                 n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
                                          ctx->pixel_counter.as<unsigned int>(), threads,
                                          (uint32_t)ctx->tune.mk_wait, (uint32_t)ctx->tune.mk_leaf,   // 0 = per-mode default
-                                         ctx->sm_count, ctx->stream);
+                                         ctx->tune.no_both != 0, ctx->sm_count, ctx->stream);
                 if (forced) break;
             }
             if (n < 0) cudaGetLastError();

@@ -110,7 +110,7 @@ int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple o
 // falls back to v1)
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
-                         int sm_count, cudaStream_t stream);
+                         bool no_both, int sm_count, cudaStream_t stream);
 size_t wavefront_state_bytes(size_t slots);
 void wavefront_bind(WavefrontParams& w, void* state, size_t slots);
 // persistent per-CTA wavefront (cta_wavefront.cu): number of path slots it needs, and the launch

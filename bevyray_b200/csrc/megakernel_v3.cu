@@ -145,6 +145,40 @@ __device__ __forceinline__ uint32_t sort4_park(uint32_t k0, uint32_t k1, uint32_
     return k0;
 }
 
+// One visit of a 4-wide fp32 record (scene_kernels.cu: build_nodes4_ch_kernel):
+//   q0..q3 = (c.x, c.y, h.x, h.y) of child 0..3, q4 / q5 = (c.z, c.z', h.z, h.z') of children 0,1 / 2,3, rr = the four refs.
+// Per axis pair: tc = c/d - o/d, lo = tc - h |1/d|, hi = tc + h |1/d| — 18 FFMA2 for the four boxes (ptxas folds the
+// negation, the absolute value and the (z, z) broadcast into the instruction).  Keys = 21 bits of entry distance | 11
+// bits of ref; the three farther children are parked, the nearest ref is returned (S4_NONE when nothing was entered).
+__device__ __forceinline__ uint32_t visit4(const float4 q0, const float4 q1, const float4 q2, const float4 q3, const float4 q4,
+                                           const float4 q5, const float4 rr, const u64 inv_xy, const u64 noi_xy, const float inv_z,
+                                           const float noi_z, const float closest_t, uint32_t& sp_addr, const uint32_t stride) {
+    float ix, iy;
+    upk2(inv_xy, ix, iy);
+    const u64 a_xy = pk2(fabsf(ix), fabsf(iy));
+    const u64 i_zz = pk2(inv_z, inv_z), n_zz = pk2(noi_z, noi_z), a_zz = pk2(fabsf(inv_z), fabsf(inv_z));
+    const u64 t0 = ffma2(pk2(q0.x, q0.y), inv_xy, noi_xy), t1 = ffma2(pk2(q1.x, q1.y), inv_xy, noi_xy);
+    const u64 t2 = ffma2(pk2(q2.x, q2.y), inv_xy, noi_xy), t3 = ffma2(pk2(q3.x, q3.y), inv_xy, noi_xy);
+    const u64 tz01 = ffma2(pk2(q4.x, q4.y), i_zz, n_zz), tz23 = ffma2(pk2(q5.x, q5.y), i_zz, n_zz);
+    float lx0, ly0, lx1, ly1, lx2, ly2, lx3, ly3, lz0, lz1, lz2, lz3;
+    float hx0, hy0, hx1, hy1, hx2, hy2, hx3, hy3, hz0, hz1, hz2, hz3;
+    upk2(ffma2(pk2(-q0.z, -q0.w), a_xy, t0), lx0, ly0); upk2(ffma2(pk2(q0.z, q0.w), a_xy, t0), hx0, hy0);
+    upk2(ffma2(pk2(-q1.z, -q1.w), a_xy, t1), lx1, ly1); upk2(ffma2(pk2(q1.z, q1.w), a_xy, t1), hx1, hy1);
+    upk2(ffma2(pk2(-q2.z, -q2.w), a_xy, t2), lx2, ly2); upk2(ffma2(pk2(q2.z, q2.w), a_xy, t2), hx2, hy2);
+    upk2(ffma2(pk2(-q3.z, -q3.w), a_xy, t3), lx3, ly3); upk2(ffma2(pk2(q3.z, q3.w), a_xy, t3), hx3, hy3);
+    upk2(ffma2(pk2(-q4.z, -q4.w), a_zz, tz01), lz0, lz1); upk2(ffma2(pk2(q4.z, q4.w), a_zz, tz01), hz0, hz1);
+    upk2(ffma2(pk2(-q5.z, -q5.w), a_zz, tz23), lz2, lz3); upk2(ffma2(pk2(q5.z, q5.w), a_zz, tz23), hz2, hz3);
+    const float e0 = fmaxf(fmaxf(lx0, ly0), fmaxf(lz0, 0.0f)), x0 = fminf(fminf(hx0, hy0), fminf(hz0, closest_t));
+    const float e1 = fmaxf(fmaxf(lx1, ly1), fmaxf(lz1, 0.0f)), x1 = fminf(fminf(hx1, hy1), fminf(hz1, closest_t));
+    const float e2 = fmaxf(fmaxf(lx2, ly2), fmaxf(lz2, 0.0f)), x2 = fminf(fminf(hx2, hy2), fminf(hz2, closest_t));
+    const float e3 = fmaxf(fmaxf(lx3, ly3), fmaxf(lz3, 0.0f)), x3 = fminf(fminf(hx3, hy3), fminf(hz3, closest_t));
+    const uint32_t k0 = e0 <= x0 ? ((__float_as_uint(e0) & ~0x7ffu) | __float_as_uint(rr.x)) : 0xffffffffu;
+    const uint32_t k1 = e1 <= x1 ? ((__float_as_uint(e1) & ~0x7ffu) | __float_as_uint(rr.y)) : 0xffffffffu;
+    const uint32_t k2 = e2 <= x2 ? ((__float_as_uint(e2) & ~0x7ffu) | __float_as_uint(rr.z)) : 0xffffffffu;
+    const uint32_t k3 = e3 <= x3 ? ((__float_as_uint(e3) & ~0x7ffu) | __float_as_uint(rr.w)) : 0xffffffffu;
+    return sort4_park(k0, k1, k2, k3, sp_addr, stride) & 0x7ffu;   // 0xffffffff (nothing entered) decodes to NONE
+}
+
 #define S4_LEAF 0x400u
 #define S4_NONE 0x7ffu      // == (0xffffffff & S4_REF_MASK): a key that was not entered decodes to NONE by itself
 #define S4_REF_MASK 0x7ffu
@@ -170,11 +204,12 @@ template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, unsigned int* __restrict__ pixel_counter,
                                                          const uint32_t n_inner, const uint32_t n_models,
                                                          const Tuning tune) {
-    constexpr bool SMEM_SCENE = MODE == 0 || MODE == 4 || MODE == 5;
-    constexpr bool TIGHT = MODE == 5;
+    constexpr bool SMEM_SCENE = MODE == 0 || MODE == 4 || MODE == 5 || MODE == 6;
+    constexpr bool TIGHT = MODE == 5 || MODE == 6;
+    constexpr bool BOTH = MODE == 6;          // tight AND reference records staged in shared memory
     constexpr bool Q16 = MODE == 2 || MODE == 3;
     constexpr bool W4 = MODE == 3;
-    constexpr bool S4 = MODE == 4 || MODE == 5;
+    constexpr bool S4 = MODE == 4 || MODE == 5 || MODE == 6;
     constexpr bool STACK4 = Q16 || S4;        // 4-byte stack entries
     constexpr uint32_t NONE = Q16 ? Q16_NONE : (S4 ? S4_NONE : V3_NONE);
     extern __shared__ float4 smem[];
@@ -187,15 +222,18 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     if (SMEM_SCENE) {
         const uint32_t rec4 = S4 ? 7u : 4u;   // float4 per inner node
         float4* sm_pairs = sm_cursor;     sm_cursor += rec4 * n_inner;
+        float4* sm_ref = sm_cursor;       if (BOTH) sm_cursor += rec4 * n_inner;
         float4* sm_spheres = sm_cursor;   sm_cursor += n_models;
         float4* sm_materials = sm_cursor; sm_cursor += 2u * sv.n_materials;
         uint32_t* sm_matid = reinterpret_cast<uint32_t*>(sm_cursor);
         sm_cursor += (n_models + 3u) / 4u;
         for (uint32_t i = tid; i < rec4 * n_inner; i += THREADS) sm_pairs[i] = TIGHT ? p.scene.nodes4_tight[i] : (S4 ? p.scene.nodes4_ch[i] : p.scene.pairs_ch[i]);
+        if (BOTH) for (uint32_t i = tid; i < rec4 * n_inner; i += THREADS) sm_ref[i] = p.scene.nodes4_ch[i];
         for (uint32_t i = tid; i < n_models; i += THREADS) sm_spheres[i] = p.scene.spheres[i];
         for (uint32_t i = tid; i < 2u * sv.n_materials; i += THREADS) sm_materials[i] = p.scene.materials[i];
         for (uint32_t i = tid; i < n_models; i += THREADS) sm_matid[i] = p.scene.sphere_material[i];
         sv.pairs_ch = sm_pairs;
+        if (BOTH) sv.pairs = sm_ref;      // (MODE 6 only: the staged reference records)
         sv.spheres = sm_spheres;
         sv.materials = sm_materials;
         sv.sphere_material = sm_matid;
@@ -216,6 +254,9 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     bool far_ray = false;   // MODE 5: this ray walks the reference boxes
     const uint32_t s_pairs = SMEM_SCENE ? opaque(smem_addr(sv.pairs_ch)) : 0u;
     const float4* const g_pairs = sv.pairs_ch;   // MODE 5: the staged tight records through a generic pointer
+    const uint32_t s_pairs_ref = BOTH ? opaque(smem_addr(sv.pairs)) : 0u;
+    const uint32_t s_spheres = SMEM_SCENE ? opaque(smem_addr(sv.spheres)) : 0u;
+    uint32_t s_rec = s_pairs;                    // S4: shared-window address of the records this ray walks
 
     const uint32_t tiles_x = (cam.width + 7u) / 8u, tiles_y = (p.shard.rows + 3u) / 4u;
     const uint32_t total_slots = tiles_x * tiles_y * 32u;
@@ -435,6 +476,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                     far_ray = far_ray || !(dx * dx + dy * dy + dz * dz <= gr.w);
                 }
                 rec_base = far_ray ? sv.nodes4_ch : g_pairs;
+                if (BOTH) s_rec = far_ray ? s_pairs_ref : s_pairs;
             }
             a = vdot(ray.d, ray.d);
             closest.t = BVR_INF;
@@ -447,6 +489,72 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         }
 
         // ======================= phase B: traversal =======================
+        if constexpr (S4) {
+            // Scenes staged in shared memory as 4-wide records.  A lane's traversal state IS (cur, pending, stack):
+            //   cur < S4_LEAF inner record to visit, S4_LEAF <= cur < S4_NONE a leaf, S4_NONE nothing in hand;
+            //   pending = a parked leaf (tested with the others' once a lane cannot go on without its test).
+            // A lane with nothing in hand, nothing parked and an empty stack is idle: its ray is finished (or it has
+            // none); idle lanes fall through every step without a state test.
+            const bool had_ray = state == TRAVERSE;
+            for (;;) {
+#pragma unroll
+                for (int rep = 0; rep < BVR_STEPS_PER_VOTE; rep++) {
+                    uint32_t c = cur;
+                    if (c < S4_LEAF) {
+                        float4 q0, q1, q2, q3, q4, q5, rr;
+                        if constexpr (TIGHT && !BOTH && BVR_FAR_GENERIC) {
+                            // one generic pointer per ray: LD resolves the shared / global window itself
+                            const float4* nd = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(rec_base) + c * 112u);
+                            q0 = nd[0]; q1 = nd[1]; q2 = nd[2]; q3 = nd[3]; q4 = nd[4]; q5 = nd[5]; rr = nd[6];
+                        } else if (TIGHT && !BOTH && far_ray) {
+                            const float4* nd = sv.nodes4_ch + 7u * c;
+                            q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2); q3 = __ldg(nd + 3);
+                            q4 = __ldg(nd + 4); q5 = __ldg(nd + 5); rr = __ldg(nd + 6);
+                        } else {
+                            const uint32_t na = (BOTH ? s_rec : s_pairs) + c * 112u;
+                            q0 = lds128(na); q1 = lds128(na + 16u); q2 = lds128(na + 32u);
+                            q3 = lds128(na + 48u); q4 = lds128(na + 64u); q5 = lds128(na + 80u);
+                            rr = lds128(na + 96u);
+                        }
+                        c = visit4(q0, q1, q2, q3, q4, q5, rr, inv_xy, noi_xy, inv.z, noi.z, closest.t, sp_addr, STACK_STRIDE);
+                    }
+                    if (c >= S4_LEAF) {
+                        if (c != S4_NONE && pending == S4_NONE) { pending = c; c = S4_NONE; }   // park the leaf, go on
+                        if (c == S4_NONE) {
+                            // pop until an entry survives the cull (a culled entry costs ~5 instructions here)
+                            while (sp_addr != s_stack0) {
+                                sp_addr -= STACK_STRIDE;
+                                const uint32_t e = lds32(sp_addr);
+                                if (__uint_as_float(e & ~S4_REF_MASK) < closest.t) { c = e & S4_REF_MASK; break; }
+                            }
+                        }
+                    }
+                    cur = c;
+                }
+                // a lane is blocked when it cannot go on without the sphere test of its parked leaf: it holds a second
+                // leaf, or has nothing else left
+                const bool parked = pending != S4_NONE;
+                const unsigned trav = __ballot_sync(full, cur != S4_NONE || parked);
+                if (trav == 0u) break;
+                const unsigned blk = __ballot_sync(full, parked && cur >= S4_LEAF);
+                if (blk != 0u) {
+                    const uint32_t nblk = (uint32_t)__popc(blk);
+                    if (nblk >= tune.leaf_batch_lanes || nblk == (uint32_t)__popc(trav)) {
+                        if (parked) {
+                            const uint32_t m = pending & 0x3ffu;      // one sphere per leaf in these layouts
+                            test_sphere(sv, ray, a, m, lds128(s_spheres + m * 16u), closest);
+                            pending = S4_NONE;
+                        }
+                    }
+                }
+                if (32u - (uint32_t)__popc(trav) >= tune.shade_wait_lanes) {
+                    // idle lanes are waiting to shade or out of pixels; only the former justify phase A
+                    const unsigned waiting = __ballot_sync(full, had_ray && cur == S4_NONE && !parked);
+                    if ((uint32_t)__popc(waiting) >= tune.shade_wait_lanes) break;
+                }
+            }
+            if (had_ray && cur == S4_NONE && pending == S4_NONE) state = SHADE;   // traversal finished
+        } else
         for (;;) {
             bool blocked = false;
 #pragma unroll
@@ -455,49 +563,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                     uint32_t c = cur;
                     if (Q16 ? c < Q16_LEAF : (S4 ? c < S4_LEAF : c < V3_NONE)) {  // inner node: test its children
                         if constexpr (S4) {
-                            // four children: key = 21 bits of entry distance | 11 bits of ref.  Record layout (scene_kernels.cu):
-                            // q0..q3 = (c.x, c.y, h.x, h.y) of child 0..3, q4 / q5 = (c.z, c.z', h.z, h.z') of children 0,1 / 2,3.
-                            float4 q0, q1, q2, q3, q4, q5, rr;
-                            if constexpr (TIGHT && BVR_FAR_GENERIC) {
-                                // one generic pointer per ray: LD resolves the shared / global window itself
-                                const float4* nd = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(rec_base) + c * 112u);
-                                q0 = nd[0]; q1 = nd[1]; q2 = nd[2]; q3 = nd[3]; q4 = nd[4]; q5 = nd[5]; rr = nd[6];
-                            } else if (TIGHT && far_ray) {
-                                const float4* nd = sv.nodes4_ch + 7u * c;
-                                q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2); q3 = __ldg(nd + 3);
-                                q4 = __ldg(nd + 4); q5 = __ldg(nd + 5); rr = __ldg(nd + 6);
-                            } else {
-                                const uint32_t na = s_pairs + c * 112u;
-                                q0 = lds128(na); q1 = lds128(na + 16u); q2 = lds128(na + 32u);
-                                q3 = lds128(na + 48u); q4 = lds128(na + 64u); q5 = lds128(na + 80u);
-                                rr = lds128(na + 96u);
-                            }
-                            // per axis pair: tc = c/d - o/d, lo = tc - h |1/d|, hi = tc + h |1/d|: 18 FFMA2 for four boxes
-                            float ix, iy;
-                            upk2(inv_xy, ix, iy);
-                            const u64 a_xy = pk2(fabsf(ix), fabsf(iy));
-                            const u64 i_zz = pk2(inv.z, inv.z), n_zz = pk2(noi.z, noi.z), a_zz = pk2(fabsf(inv.z), fabsf(inv.z));
-                            const u64 t0 = ffma2(pk2(q0.x, q0.y), inv_xy, noi_xy), t1 = ffma2(pk2(q1.x, q1.y), inv_xy, noi_xy);
-                            const u64 t2 = ffma2(pk2(q2.x, q2.y), inv_xy, noi_xy), t3 = ffma2(pk2(q3.x, q3.y), inv_xy, noi_xy);
-                            const u64 tz01 = ffma2(pk2(q4.x, q4.y), i_zz, n_zz), tz23 = ffma2(pk2(q5.x, q5.y), i_zz, n_zz);
-                            float lx0, ly0, lx1, ly1, lx2, ly2, lx3, ly3, lz0, lz1, lz2, lz3;
-                            float hx0, hy0, hx1, hy1, hx2, hy2, hx3, hy3, hz0, hz1, hz2, hz3;
-                            upk2(ffma2(pk2(-q0.z, -q0.w), a_xy, t0), lx0, ly0); upk2(ffma2(pk2(q0.z, q0.w), a_xy, t0), hx0, hy0);
-                            upk2(ffma2(pk2(-q1.z, -q1.w), a_xy, t1), lx1, ly1); upk2(ffma2(pk2(q1.z, q1.w), a_xy, t1), hx1, hy1);
-                            upk2(ffma2(pk2(-q2.z, -q2.w), a_xy, t2), lx2, ly2); upk2(ffma2(pk2(q2.z, q2.w), a_xy, t2), hx2, hy2);
-                            upk2(ffma2(pk2(-q3.z, -q3.w), a_xy, t3), lx3, ly3); upk2(ffma2(pk2(q3.z, q3.w), a_xy, t3), hx3, hy3);
-                            upk2(ffma2(pk2(-q4.z, -q4.w), a_zz, tz01), lz0, lz1); upk2(ffma2(pk2(q4.z, q4.w), a_zz, tz01), hz0, hz1);
-                            upk2(ffma2(pk2(-q5.z, -q5.w), a_zz, tz23), lz2, lz3); upk2(ffma2(pk2(q5.z, q5.w), a_zz, tz23), hz2, hz3);
-                            const float e0 = fmaxf(fmaxf(lx0, ly0), fmaxf(lz0, 0.0f)), x0 = fminf(fminf(hx0, hy0), fminf(hz0, closest.t));
-                            const float e1 = fmaxf(fmaxf(lx1, ly1), fmaxf(lz1, 0.0f)), x1 = fminf(fminf(hx1, hy1), fminf(hz1, closest.t));
-                            const float e2 = fmaxf(fmaxf(lx2, ly2), fmaxf(lz2, 0.0f)), x2 = fminf(fminf(hx2, hy2), fminf(hz2, closest.t));
-                            const float e3 = fmaxf(fmaxf(lx3, ly3), fmaxf(lz3, 0.0f)), x3 = fminf(fminf(hx3, hy3), fminf(hz3, closest.t));
-                            uint32_t k0 = e0 <= x0 ? ((__float_as_uint(e0) & ~S4_REF_MASK) | __float_as_uint(rr.x)) : 0xffffffffu;
-                            uint32_t k1 = e1 <= x1 ? ((__float_as_uint(e1) & ~S4_REF_MASK) | __float_as_uint(rr.y)) : 0xffffffffu;
-                            uint32_t k2 = e2 <= x2 ? ((__float_as_uint(e2) & ~S4_REF_MASK) | __float_as_uint(rr.z)) : 0xffffffffu;
-                            uint32_t k3 = e3 <= x3 ? ((__float_as_uint(e3) & ~S4_REF_MASK) | __float_as_uint(rr.w)) : 0xffffffffu;
-                            k0 = sort4_park(k0, k1, k2, k3, sp_addr, STACK_STRIDE);
-                            c = k0 & S4_REF_MASK;   // 0xffffffff (nothing entered) decodes to NONE
+                            // (scenes staged as 4-wide records run the loop above)
                         } else if constexpr (W4) {
                             // four children: key = 11 bits of entry distance | 21 bits of ref, 0xffffffff = not entered
                             uint4 qa, qb, qc, qd;
@@ -613,21 +679,25 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
 
 template <int THREADS>
 int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
-              unsigned int* pixel_counter, Tuning tune, int sm_count, cudaStream_t stream) {
+              unsigned int* pixel_counter, Tuning tune, bool no_both, int sm_count, cudaStream_t stream) {
     uint32_t stack_cap = tree_depth + 1u;
     size_t scene_bytes = (size_t)(4u * n_inner + n_models + 2u * p.scene.n_materials + (n_models + 3u) / 4u) * 16u;
     const size_t max_smem = 227u * 1024u;
-    // 4-wide fp32 records in shared memory when they and their 4-byte stacks fit
-    const uint32_t cap4 = 3u * ((tree_depth + 1u) / 2u) + 2u;
+    // 4-wide fp32 records in shared memory when they and their 4-byte stacks fit.  A 4-wide visit parks at most three
+    // siblings and descends two levels of the uploaded tree; inner records sit on levels 1, 3, 5, ... <= depth - 1.
+    const uint32_t cap4 = 3u * (tree_depth / 2u) + 1u;
     const size_t scene4_bytes = scene_bytes + (size_t)3u * n_inner * 16u;
     const bool s4 = p.scene.nodes4_ch != nullptr && scene4_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t) <= max_smem;
     const bool tight = s4 && p.scene.nodes4_tight != nullptr;
+    // ... and the reference records next to the tight ones when that fits too (far rays then stay in shared memory)
+    const size_t both_bytes = scene4_bytes + (size_t)7u * n_inner * 16u;
+    const bool both = tight && !no_both && both_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t) <= max_smem;
     if (s4) {
         // tuned on C2 (profiles/r01_tuning_sweeps.txt): the 4-wide walk wants later shading and immediate leaf tests
         if (tune.shade_wait_lanes == 0u) tune.shade_wait_lanes = 29u;
         if (tune.leaf_batch_lanes == 0u) tune.leaf_batch_lanes = 1u;
-        const size_t smem4 = scene4_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t);
-        auto k4 = tight ? megakernel_v3<THREADS, 5> : megakernel_v3<THREADS, 4>;
+        const size_t smem4 = (both ? both_bytes : scene4_bytes) + (size_t)THREADS * cap4 * sizeof(uint32_t);
+        auto k4 = both ? megakernel_v3<THREADS, 6> : (tight ? megakernel_v3<THREADS, 5> : megakernel_v3<THREADS, 4>);
         if (cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4) != cudaSuccess) return -1;
         const uint32_t tiles4 = ((p.cam.width + 7u) / 8u) * ((p.shard.rows + 3u) / 4u);
         uint32_t grid4 = (uint32_t)sm_count;
@@ -667,15 +737,15 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
 
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
-                         int sm_count, cudaStream_t stream) {
+                         bool no_both, int sm_count, cudaStream_t stream) {
     if (p.cam.width > 0xffffu || p.shard.rows > 0xffffu) return -1;   // pixel packed as px | ly << 16
     Tuning t{shade_wait_lanes, leaf_batch_lanes};
     switch (threads) {
-        case 256: return launch_v3<256>(p, n_inner, n_models, tree_depth, pixel_counter, t, sm_count, stream);
-        case 512: return launch_v3<512>(p, n_inner, n_models, tree_depth, pixel_counter, t, sm_count, stream);
-        case 768: return launch_v3<768>(p, n_inner, n_models, tree_depth, pixel_counter, t, sm_count, stream);
-        case 896: return launch_v3<896>(p, n_inner, n_models, tree_depth, pixel_counter, t, sm_count, stream);
-        case 1024: return launch_v3<1024>(p, n_inner, n_models, tree_depth, pixel_counter, t, sm_count, stream);
+        case 256: return launch_v3<256>(p, n_inner, n_models, tree_depth, pixel_counter, t, no_both, sm_count, stream);
+        case 512: return launch_v3<512>(p, n_inner, n_models, tree_depth, pixel_counter, t, no_both, sm_count, stream);
+        case 768: return launch_v3<768>(p, n_inner, n_models, tree_depth, pixel_counter, t, no_both, sm_count, stream);
+        case 896: return launch_v3<896>(p, n_inner, n_models, tree_depth, pixel_counter, t, no_both, sm_count, stream);
+        case 1024: return launch_v3<1024>(p, n_inner, n_models, tree_depth, pixel_counter, t, no_both, sm_count, stream);
         default: return -1;
     }
 }

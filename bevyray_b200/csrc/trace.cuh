@@ -104,28 +104,30 @@ __device__ __forceinline__ float ray_bounding_dst(V3 o, V3 inv, float mnx, float
     return hit ? (t_near > 0.0f ? t_near : 0.0f) : BVR_INF;
 }
 
-// raytrace.wgsl:371-383 with a = dot(d,d) hoisted; raytrace.wgsl:353-354 acceptance test
+// raytrace.wgsl:371-383 with a = dot(d,d) hoisted; raytrace.wgsl:353-354 acceptance test.  `sp` = (centre, radius) of
+// model i, loaded by the caller (shared memory or global).
+__device__ __forceinline__ void test_sphere(const SceneView& s, const Ray& ray, float a, uint32_t i, const float4 sp, Hit& closest) {
+    const V3 oc = v3(fsub(sp.x, ray.o.x), fsub(sp.y, ray.o.y), fsub(sp.z, ray.o.z));
+    const float h = vdot(ray.d, oc);
+    const float c = fsub(vdot(oc, oc), fmul(sp.w, sp.w));
+    const float disc = fsub(fmul(h, h), fmul(a, c));
+    if (disc < 0.0f) return;                         // hit_sphere returns -1.0
+    const float t = fdiv(fsub(h, fsqrt(disc)), a);
+    if (t != -1.0f && t > 0.001f) {
+        if (t < closest.t) { closest.t = t; closest.model = i; }
+        // Bit-exact tie between two spheres (a small sphere resting on the ground sphere, duplicates): the
+        // reference keeps the one it reaches FIRST (strict <, raytrace.wgsl:354), and its order over the
+        // leaves is fixed by the tree — right subtree first.  Any other visiting order reproduces that choice
+        // by preferring the lower rank.
+        else if (t == closest.t && i != closest.model && s.model_rank &&
+                 s.model_rank[i] < s.model_rank[closest.model]) closest.model = i;
+    }
+}
+
 __device__ __forceinline__ void test_leaf(const SceneView& s, const Ray& ray, float a, uint32_t ref, Hit& closest) {
     const uint32_t first = ref & BVR_LEAF_FIRST_MASK;
     const uint32_t count = ((ref >> 24) & 0x7fu) + 1u;
-    for (uint32_t i = first; i < first + count; i++) {
-        const float4 sp = s.spheres[i];
-        const V3 oc = v3(fsub(sp.x, ray.o.x), fsub(sp.y, ray.o.y), fsub(sp.z, ray.o.z));
-        const float h = vdot(ray.d, oc);
-        const float c = fsub(vdot(oc, oc), fmul(sp.w, sp.w));
-        const float disc = fsub(fmul(h, h), fmul(a, c));
-        if (disc < 0.0f) continue;                       // hit_sphere returns -1.0
-        const float t = fdiv(fsub(h, fsqrt(disc)), a);
-        if (t != -1.0f && t > 0.001f) {
-            if (t < closest.t) { closest.t = t; closest.model = i; }
-            // Bit-exact tie between two spheres (a small sphere resting on the ground sphere, duplicates): the
-            // reference keeps the one it reaches FIRST (strict <, raytrace.wgsl:354), and its order over the
-            // leaves is fixed by the tree — right subtree first.  Any other visiting order reproduces that choice
-            // by preferring the lower rank.
-            else if (t == closest.t && i != closest.model && s.model_rank &&
-                     s.model_rank[i] < s.model_rank[closest.model]) closest.model = i;
-        }
-    }
+    for (uint32_t i = first; i < first + count; i++) test_sphere(s, ray, a, i, s.spheres[i], closest);
 }
 
 // raytrace.wgsl:313-346 verbatim control flow: LIFO stack, first child pushed first, no ordering,
