@@ -84,7 +84,7 @@ class BvrOutputs(C.Structure):
 class BvrStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("last_render_ms", C.c_float),
-                ("last_upload_ms", C.c_float)]
+                ("last_upload_ms", C.c_float), ("selfcheck_rays", C.c_uint64), ("selfcheck_mismatches", C.c_uint64)]
 
 
 class BvrhStandardMaterial(C.Structure):

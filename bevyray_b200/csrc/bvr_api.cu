@@ -100,8 +100,9 @@ struct BvrContext {
     DeviceBuffer in_rgba, in_depth, out_rgba, out_rt_depth, out_id, out_pdepth, out_srgb8;
     PinnedBuffer io_staging;
 
-    DeviceBuffer ray_counter;
-    unsigned long long* ray_counter_host = nullptr;   // pinned
+    DeviceBuffer selfcheck_log;               // BVR_SELFCHECK: logged rays + their count
+    DeviceBuffer ray_counter;                 // [0] rays, [1] self-check rays, [2] self-check disagreements
+    unsigned long long* ray_counter_host = nullptr;   // pinned, 3 words
     cudaEvent_t ev_render0 = nullptr, ev_render1 = nullptr, ev_upload0 = nullptr, ev_upload1 = nullptr;
     bool render_timed = false, upload_timed = false;
     BvrStats stats{};
@@ -323,11 +324,11 @@ int bvr_create(int device, BvrContext** out_ctx) {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_upload0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_upload1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->upload_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = ctx->ray_counter.ensure(sizeof(unsigned long long));
+    if (e == cudaSuccess) e = ctx->ray_counter.ensure(3 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = ctx->root_ref.ensure(sizeof(uint32_t));
     if (e == cudaSuccess) e = ctx->pixel_counter.ensure(sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->ray_counter_host, sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->ray_counter_host, 3 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->wf_host_counts, 8 * sizeof(unsigned int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->depth_host, sizeof(unsigned int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->q16_bad_host, sizeof(unsigned int), cudaHostAllocDefault);
@@ -339,7 +340,7 @@ int bvr_create(int device, BvrContext** out_ctx) {
         bvr_destroy(ctx);
         return e == cudaErrorMemoryAllocation ? BVR_ERR_OUT_OF_MEMORY : BVR_ERR_CUDA;
     }
-    *ctx->ray_counter_host = 0;
+    ctx->ray_counter_host[0] = ctx->ray_counter_host[1] = ctx->ray_counter_host[2] = 0;
     ctx->stream = ctx->own_stream;
     ctx->tune = read_env_tuning();
     *out_ctx = ctx;
@@ -353,7 +354,7 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->pairs_ch, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->validate_scratch, &ctx->validate_out, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->selfcheck_log, &ctx->validate_scratch, &ctx->validate_out, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
@@ -765,7 +766,18 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
     p.out_primary_depth = out->primary_depth;
     p.out_srgb8 = reinterpret_cast<uchar4*>(out->srgb8);
 
-    BVR_CK(cudaMemsetAsync(ctx->ray_counter.ptr, 0, sizeof(unsigned long long), ctx->stream));
+    BVR_CK(cudaMemsetAsync(ctx->ray_counter.ptr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    // the self-check walks the uploaded tree in reference order: pointless (and truncating) on trees the reference-order
+    // kernel renders anyway
+    p.selfcheck_log = nullptr;
+    if (ctx->tune.selfcheck && !p.reference_order) {
+        const uint32_t cap = 1u << 20;                       // 32 MB of log; a frame of 1 G rays logs about that many
+        BVR_CK(ctx->selfcheck_log.ensure((size_t)cap * 32u + 16u));
+        p.selfcheck_count = reinterpret_cast<unsigned int*>(ctx->selfcheck_log.as<char>() + (size_t)cap * 32u);
+        BVR_CK(cudaMemsetAsync(p.selfcheck_count, 0, sizeof(unsigned int), ctx->stream));
+        p.selfcheck_log = ctx->selfcheck_log.as<float4>();
+        p.selfcheck_cap = cap;
+    }
     BVR_CK(cudaEventRecord(ctx->ev_render0, ctx->stream));
     int launches = 0;
     if (p.cam.level == 0u) {
@@ -811,10 +823,11 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
         }
         if (n < 0) n = launch_megakernel(p, ctx->stream);   // reference-order traversal, or scene too deep
         launches += n;
+        launches += launch_selfcheck(p, ctx->ray_counter.as<unsigned long long>() + 1, ctx->stream);
     }
     BVR_CK(cudaGetLastError());
     BVR_CK(cudaEventRecord(ctx->ev_render1, ctx->stream));
-    BVR_CK(cudaMemcpyAsync(ctx->ray_counter_host, ctx->ray_counter.ptr, sizeof(unsigned long long),
+    BVR_CK(cudaMemcpyAsync(ctx->ray_counter_host, ctx->ray_counter.ptr, 3 * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost, ctx->stream));
     ctx->render_timed = true;
     ctx->stats.kernel_launches += (uint64_t)launches;
@@ -963,7 +976,9 @@ int bvr_get_stats(BvrContext* ctx, BvrStats* out) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->ev_render0, ctx->ev_render1) == cudaSuccess) ctx->stats.last_render_ms = ms;
         else cudaGetLastError();
-        ctx->stats.rays = *ctx->ray_counter_host;
+        ctx->stats.rays = ctx->ray_counter_host[0];
+        ctx->stats.selfcheck_rays = ctx->ray_counter_host[1];
+        ctx->stats.selfcheck_mismatches = ctx->ray_counter_host[2];
     }
     if (ctx->upload_timed) {
         float ms = 0;

@@ -28,6 +28,9 @@ struct RenderParams {
     uchar4* out_srgb8;
     unsigned long long* ray_counter;   // += raycast() invocations
     uint32_t reference_order;          // BvrTraversal
+    float4* selfcheck_log;             // BVR_SELFCHECK: 2 x float4 per logged ray (o.xyz, t) (d.xyz, model bits), or null
+    unsigned int* selfcheck_count;     // rays logged so far (may exceed the capacity: the excess is dropped)
+    uint32_t selfcheck_cap;
 };
 
 // Wavefront path state in HBM (SoA, indexed by shard-local pixel slot) and the work queues.
@@ -111,6 +114,8 @@ int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple o
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
                          bool no_both, int sm_count, cudaStream_t stream);
+// BVR_SELFCHECK: re-traces the rays the render kernel logged, in reference order; counters = {checked, disagreements}
+int launch_selfcheck(const RenderParams& p, unsigned long long* counters, cudaStream_t stream);
 size_t wavefront_state_bytes(size_t slots);
 void wavefront_bind(WavefrontParams& w, void* state, size_t slots);
 // persistent per-CTA wavefront (cta_wavefront.cu): number of path slots it needs, and the launch

@@ -30,6 +30,9 @@ enum Kind : int { K_NONE = 0, K_MISS = 1, K_METAL = 2, K_GLASS = 3, K_DIFFUSE = 
 #ifndef BVR_FAR_GENERIC
 #define BVR_FAR_GENERIC 1      // MODE 5: far rays pick their records through a generic pointer (no predicated second load path)
 #endif
+#ifndef BVR_SORT_MIDDLE
+#define BVR_SORT_MIDDLE 1      // 0: the two middle children of a 4-wide visit are parked unordered (2 instructions less)
+#endif
 #ifndef BVR_STEPS_PER_VOTE
 #define BVR_STEPS_PER_VOTE 2   // traversal steps between two rounds of warp votes
 #endif
@@ -113,16 +116,24 @@ __device__ __forceinline__ bool box_cull(V3 inv, V3 ainv, V3 noi, float closest_
 // or leaves (selF) through, and ONE FFMA maps it to the ray parameter: t = (2^23 + q) * (step/d) + C with
 // C = (base - o)/d - 2^23 * step/d.  C carries up to half a grid step of rounding error, which the extra step
 // of outward rounding in the records absorbs.  No per-axis min/max: the ray's octant picks near and far.
+// prmt.b32 without the `& 0x7777` that __byte_perm has to put in front of a selector it cannot see through
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
 __device__ __forceinline__ bool box_cull_q16(uint32_t wx, uint32_t wy, uint32_t wz, V3 sinv, V3 cq, uint32_t snx,
                                              uint32_t sny, uint32_t snz, uint32_t sfx, uint32_t sfy, uint32_t sfz,
                                              float closest_t, float& entry) {
     const uint32_t magic = 0x00004b00u;
-    const float tnx = __fmaf_rn(__uint_as_float(__byte_perm(wx, magic, snx)), sinv.x, cq.x);
-    const float tny = __fmaf_rn(__uint_as_float(__byte_perm(wy, magic, sny)), sinv.y, cq.y);
-    const float tnz = __fmaf_rn(__uint_as_float(__byte_perm(wz, magic, snz)), sinv.z, cq.z);
-    const float tfx = __fmaf_rn(__uint_as_float(__byte_perm(wx, magic, sfx)), sinv.x, cq.x);
-    const float tfy = __fmaf_rn(__uint_as_float(__byte_perm(wy, magic, sfy)), sinv.y, cq.y);
-    const float tfz = __fmaf_rn(__uint_as_float(__byte_perm(wz, magic, sfz)), sinv.z, cq.z);
+    // (near, far) of one axis share the multiplier and the constant: one FFMA2 with broadcast operands per axis
+    float tnx, tfx, tny, tfy, tnz, tfz;
+    upk2(ffma2(pk2(__uint_as_float(prmt(wx, magic, snx)), __uint_as_float(prmt(wx, magic, sfx))),
+               pk2(sinv.x, sinv.x), pk2(cq.x, cq.x)), tnx, tfx);
+    upk2(ffma2(pk2(__uint_as_float(prmt(wy, magic, sny)), __uint_as_float(prmt(wy, magic, sfy))),
+               pk2(sinv.y, sinv.y), pk2(cq.y, cq.y)), tny, tfy);
+    upk2(ffma2(pk2(__uint_as_float(prmt(wz, magic, snz)), __uint_as_float(prmt(wz, magic, sfz))),
+               pk2(sinv.z, sinv.z), pk2(cq.z, cq.z)), tnz, tfz);
     entry = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
     const float exit = fminf(fminf(tfx, tfy), fminf(tfz, closest_t));
     return entry <= exit;
@@ -131,28 +142,30 @@ __device__ __forceinline__ bool box_cull_q16(uint32_t wx, uint32_t wy, uint32_t 
 // Four children as packed keys (entry distance in the high bits, ref in the low bits; 0xffffffff = not entered):
 // sorts them with a 5-comparator network of integer min/max, parks the three farther ones (farthest first) and
 // returns the nearest.
-__device__ __forceinline__ uint32_t sort4_park(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, uint32_t& sp_addr,
-                                               const uint32_t stride) {
+template <class Push>
+__device__ __forceinline__ uint32_t sort4_park(uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3, Push push) {
     uint32_t t0;
     t0 = min(k0, k1); k1 = max(k0, k1); k0 = t0;
     t0 = min(k2, k3); k3 = max(k2, k3); k2 = t0;
     t0 = min(k0, k2); k2 = max(k0, k2); k0 = t0;
     t0 = min(k1, k3); k3 = max(k1, k3); k1 = t0;
+#if BVR_SORT_MIDDLE
     t0 = min(k1, k2); k2 = max(k1, k2); k1 = t0;
-    if (k3 != 0xffffffffu) { sts32(sp_addr, k3); sp_addr += stride; }
-    if (k2 != 0xffffffffu) { sts32(sp_addr, k2); sp_addr += stride; }
-    if (k1 != 0xffffffffu) { sts32(sp_addr, k1); sp_addr += stride; }
+#endif
+    if (k3 != 0xffffffffu) push(k3);
+    if (k2 != 0xffffffffu) push(k2);
+    if (k1 != 0xffffffffu) push(k1);
     return k0;
 }
-
 // One visit of a 4-wide fp32 record (scene_kernels.cu: build_nodes4_ch_kernel):
 //   q0..q3 = (c.x, c.y, h.x, h.y) of child 0..3, q4 / q5 = (c.z, c.z', h.z, h.z') of children 0,1 / 2,3, rr = the four refs.
 // Per axis pair: tc = c/d - o/d, lo = tc - h |1/d|, hi = tc + h |1/d| — 18 FFMA2 for the four boxes (ptxas folds the
 // negation, the absolute value and the (z, z) broadcast into the instruction).  Keys = 21 bits of entry distance | 11
 // bits of ref; the three farther children are parked, the nearest ref is returned (S4_NONE when nothing was entered).
+template <class Push>
 __device__ __forceinline__ uint32_t visit4(const float4 q0, const float4 q1, const float4 q2, const float4 q3, const float4 q4,
                                            const float4 q5, const float4 rr, const u64 inv_xy, const u64 noi_xy, const float inv_z,
-                                           const float noi_z, const float closest_t, uint32_t& sp_addr, const uint32_t stride) {
+                                           const float noi_z, const float closest_t, Push push) {
     float ix, iy;
     upk2(inv_xy, ix, iy);
     const u64 a_xy = pk2(fabsf(ix), fabsf(iy));
@@ -176,7 +189,7 @@ __device__ __forceinline__ uint32_t visit4(const float4 q0, const float4 q1, con
     const uint32_t k1 = e1 <= x1 ? ((__float_as_uint(e1) & ~0x7ffu) | __float_as_uint(rr.y)) : 0xffffffffu;
     const uint32_t k2 = e2 <= x2 ? ((__float_as_uint(e2) & ~0x7ffu) | __float_as_uint(rr.z)) : 0xffffffffu;
     const uint32_t k3 = e3 <= x3 ? ((__float_as_uint(e3) & ~0x7ffu) | __float_as_uint(rr.w)) : 0xffffffffu;
-    return sort4_park(k0, k1, k2, k3, sp_addr, stride) & 0x7ffu;   // 0xffffffff (nothing entered) decodes to NONE
+    return sort4_park(k0, k1, k2, k3, push) & 0x7ffu;   // 0xffffffff (nothing entered) decodes to NONE
 }
 
 #define S4_LEAF 0x400u
@@ -185,6 +198,26 @@ __device__ __forceinline__ uint32_t visit4(const float4 q0, const float4 q1, con
 #define Q16_LEAF 0x100000u
 #define Q16_NONE 0x200000u
 #define Q16_REF_MASK 0x1fffffu
+
+// BVR_SELFCHECK=1: a runtime witness for the culling-only shortcuts (tight boxes, 16-bit grid, FMA slab test, near-first
+// order, postponed leaf tests).  About one finished ray in 1024 is LOGGED by the render kernel (origin, direction, the
+// closest hit it found); selfcheck_kernel then traces the logged rays again with the verbatim reference-order traversal
+// on the reference's own boxes (trace.cuh: raycast_reference_order, strict arithmetic) and counts different closest hits.
+__global__ void selfcheck_kernel(const SceneView sv, const float4* __restrict__ log, const unsigned int* __restrict__ n_logged,
+                                 uint32_t cap, unsigned long long* __restrict__ counters) {
+    const uint32_t n = min(*n_logged, cap);
+    unsigned long long bad = 0, seen = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = log[2u * i], b = log[2u * i + 1u];
+        const Ray r{v3(a.x, a.y, a.z), v3(b.x, b.y, b.z)};
+        const Hit want = raycast_reference_order(sv, r);
+        const bool same = __float_as_uint(want.t) == __float_as_uint(a.w) && (want.t == BVR_INF || want.model == __float_as_uint(b.w));
+        seen++;
+        if (!same) bad++;
+    }
+    if (seen) atomicAdd(&counters[0], seen);
+    if (bad) atomicAdd(&counters[1], bad);
+}
 
 struct Tuning {
     uint32_t shade_wait_lanes;   // leave phase B when this many lanes wait for shading
@@ -275,7 +308,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     float a = 1.0f;
     Hit closest{BVR_INF, 0xffffffffu};
     uint32_t cur = NONE, pending = NONE;
-    uint32_t sp_addr = s_stack0;   // next free stack slot
+    uint32_t sp_addr = s_stack0;    // next free stack slot
     uint32_t rays = 0;
 
     for (;;) {
@@ -285,6 +318,13 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             int kind = K_NONE;
             uint32_t mid = 0;
             if (state == SHADE) {
+                if (p.selfcheck_log != nullptr && (rng & 1023u) == 0u) {
+                    const uint32_t slot = atomicAdd(p.selfcheck_count, 1u);
+                    if (slot < p.selfcheck_cap) {
+                        p.selfcheck_log[2u * slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, closest.t);
+                        p.selfcheck_log[2u * slot + 1u] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(closest.model));
+                    }
+                }
                 if (bounce == 0u) {
                     first_depth = closest.t;
                     if (sidx == 0u && (p.out_primary_id || p.out_primary_depth)) {   // first sample's primary hit
@@ -490,37 +530,44 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
 
         // ======================= phase B: traversal =======================
         if constexpr (S4) {
-            // Scenes staged in shared memory as 4-wide records.  A lane's traversal state IS (cur, pending, stack):
-            //   cur < S4_LEAF inner record to visit, S4_LEAF <= cur < S4_NONE a leaf, S4_NONE nothing in hand;
+            // 4-wide records staged in shared memory.  A lane's traversal state IS (cur, pending, stack):
+            //   cur < LEAFV inner record to visit, LEAFV <= cur < NONE a leaf, NONE nothing in hand;
             //   pending = a parked leaf (tested with the others' once a lane cannot go on without its test).
             // A lane with nothing in hand, nothing parked and an empty stack is idle: its ray is finished (or it has
             // none); idle lanes fall through every step without a state test.
+            // (The 4-wide 16-bit records of big scenes were tried in this loop too, with the deep part of the stack in local
+            // memory to free L1 for the tree: L1 hits 7 -> 21 %, L2 sectors -25 %, but +14 % instructions in an ALU-bound
+            // kernel: 462 ms against 420 ms for the general loop below — profiles/r02_tuning_sweeps.txt.)
+            constexpr uint32_t LEAFV = S4_LEAF;
+            auto push = [&](uint32_t k) { sts32(sp_addr, k); sp_addr += STACK_STRIDE; };
             const bool had_ray = state == TRAVERSE;
             for (;;) {
 #pragma unroll
                 for (int rep = 0; rep < BVR_STEPS_PER_VOTE; rep++) {
                     uint32_t c = cur;
-                    if (c < S4_LEAF) {
-                        float4 q0, q1, q2, q3, q4, q5, rr;
-                        if constexpr (TIGHT && !BOTH && BVR_FAR_GENERIC) {
-                            // one generic pointer per ray: LD resolves the shared / global window itself
-                            const float4* nd = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(rec_base) + c * 112u);
-                            q0 = nd[0]; q1 = nd[1]; q2 = nd[2]; q3 = nd[3]; q4 = nd[4]; q5 = nd[5]; rr = nd[6];
-                        } else if (TIGHT && !BOTH && far_ray) {
-                            const float4* nd = sv.nodes4_ch + 7u * c;
-                            q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2); q3 = __ldg(nd + 3);
-                            q4 = __ldg(nd + 4); q5 = __ldg(nd + 5); rr = __ldg(nd + 6);
-                        } else {
-                            const uint32_t na = (BOTH ? s_rec : s_pairs) + c * 112u;
-                            q0 = lds128(na); q1 = lds128(na + 16u); q2 = lds128(na + 32u);
-                            q3 = lds128(na + 48u); q4 = lds128(na + 64u); q5 = lds128(na + 80u);
-                            rr = lds128(na + 96u);
+                    if (c < LEAFV) {
+                        if constexpr (S4) {
+                            float4 q0, q1, q2, q3, q4, q5, rr;
+                            if constexpr (TIGHT && !BOTH && BVR_FAR_GENERIC) {
+                                // one generic pointer per ray: LD resolves the shared / global window itself
+                                const float4* nd = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(rec_base) + c * 112u);
+                                q0 = nd[0]; q1 = nd[1]; q2 = nd[2]; q3 = nd[3]; q4 = nd[4]; q5 = nd[5]; rr = nd[6];
+                            } else if (TIGHT && !BOTH && far_ray) {
+                                const float4* nd = sv.nodes4_ch + 7u * c;
+                                q0 = __ldg(nd); q1 = __ldg(nd + 1); q2 = __ldg(nd + 2); q3 = __ldg(nd + 3);
+                                q4 = __ldg(nd + 4); q5 = __ldg(nd + 5); rr = __ldg(nd + 6);
+                            } else {
+                                const uint32_t na = (BOTH ? s_rec : s_pairs) + c * 112u;
+                                q0 = lds128(na); q1 = lds128(na + 16u); q2 = lds128(na + 32u);
+                                q3 = lds128(na + 48u); q4 = lds128(na + 64u); q5 = lds128(na + 80u);
+                                rr = lds128(na + 96u);
+                            }
+                            c = visit4(q0, q1, q2, q3, q4, q5, rr, inv_xy, noi_xy, inv.z, noi.z, closest.t, push);
                         }
-                        c = visit4(q0, q1, q2, q3, q4, q5, rr, inv_xy, noi_xy, inv.z, noi.z, closest.t, sp_addr, STACK_STRIDE);
                     }
-                    if (c >= S4_LEAF) {
-                        if (c != S4_NONE && pending == S4_NONE) { pending = c; c = S4_NONE; }   // park the leaf, go on
-                        if (c == S4_NONE) {
+                    if (c >= LEAFV) {
+                        if (c != NONE && pending == NONE) { pending = c; c = NONE; }   // park the leaf, go on
+                        if (c == NONE) {
                             // pop until an entry survives the cull (a culled entry costs ~5 instructions here)
                             while (sp_addr != s_stack0) {
                                 sp_addr -= STACK_STRIDE;
@@ -533,27 +580,27 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 }
                 // a lane is blocked when it cannot go on without the sphere test of its parked leaf: it holds a second
                 // leaf, or has nothing else left
-                const bool parked = pending != S4_NONE;
-                const unsigned trav = __ballot_sync(full, cur != S4_NONE || parked);
+                const bool parked = pending != NONE;
+                const unsigned trav = __ballot_sync(full, cur != NONE || parked);
                 if (trav == 0u) break;
-                const unsigned blk = __ballot_sync(full, parked && cur >= S4_LEAF);
+                const unsigned blk = __ballot_sync(full, parked && cur >= LEAFV);
                 if (blk != 0u) {
                     const uint32_t nblk = (uint32_t)__popc(blk);
                     if (nblk >= tune.leaf_batch_lanes || nblk == (uint32_t)__popc(trav)) {
                         if (parked) {
                             const uint32_t m = pending & 0x3ffu;      // one sphere per leaf in these layouts
                             test_sphere(sv, ray, a, m, lds128(s_spheres + m * 16u), closest);
-                            pending = S4_NONE;
+                            pending = NONE;
                         }
                     }
                 }
                 if (32u - (uint32_t)__popc(trav) >= tune.shade_wait_lanes) {
                     // idle lanes are waiting to shade or out of pixels; only the former justify phase A
-                    const unsigned waiting = __ballot_sync(full, had_ray && cur == S4_NONE && !parked);
+                    const unsigned waiting = __ballot_sync(full, had_ray && cur == NONE && !parked);
                     if ((uint32_t)__popc(waiting) >= tune.shade_wait_lanes) break;
                 }
             }
-            if (had_ray && cur == S4_NONE && pending == S4_NONE) state = SHADE;   // traversal finished
+            if (had_ray && cur == NONE && pending == NONE) state = SHADE;   // traversal finished
         } else
         for (;;) {
             bool blocked = false;
@@ -579,7 +626,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                                               ? (((__float_as_uint(e) >> 20) << 21) | qc.w) : 0xffffffffu;
                             uint32_t k3 = box_cull_q16(qd.x, qd.y, qd.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
                                               ? (((__float_as_uint(e) >> 20) << 21) | qd.w) : 0xffffffffu;
-                            k0 = sort4_park(k0, k1, k2, k3, sp_addr, STACK_STRIDE);
+                            k0 = sort4_park(k0, k1, k2, k3, [&](uint32_t k) { sts32(sp_addr, k); sp_addr += STACK_STRIDE; });
                             c = k0 != 0xffffffffu ? (k0 & Q16_REF_MASK) : NONE;
                         } else {
                           // two children
@@ -714,7 +761,7 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
     // lanes is 622 -> 414 ms, profiles/r01_tuning_sweeps.txt)
     if (tune.shade_wait_lanes == 0u) tune.shade_wait_lanes = smem_scene ? 26u : 8u;
     if (tune.leaf_batch_lanes == 0u) tune.leaf_batch_lanes = smem_scene ? 4u : 1u;
-    if (w4) stack_cap = 3u * ((tree_depth + 1u) / 2u) + 2u;       // up to three siblings parked per 4-wide level
+    if (w4) stack_cap = 3u * (tree_depth / 2u) + 1u;              // up to three siblings parked per 4-wide level
     const size_t stack_bytes = (size_t)THREADS * stack_cap * (q16 ? sizeof(uint32_t) : sizeof(uint2));
     const size_t smem = (smem_scene ? scene_bytes : 0) + stack_bytes;
     if (smem > max_smem) return -1;
@@ -734,6 +781,12 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
 }
 
 }  // namespace
+
+int launch_selfcheck(const RenderParams& p, unsigned long long* counters, cudaStream_t stream) {
+    if (!p.selfcheck_log) return 0;
+    selfcheck_kernel<<<296, 256, 0, stream>>>(p.scene, p.selfcheck_log, p.selfcheck_count, p.selfcheck_cap, counters);
+    return 1;
+}
 
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,

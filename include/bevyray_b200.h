@@ -195,6 +195,11 @@ typedef struct BvrStats {
     uint64_t d2h_bytes;       /* bytes copied device->host since bvr_create */
     float    last_render_ms;  /* device time of the last render (CUDA events on the context stream) */
     float    last_upload_ms;
+    /* BVR_SELFCHECK=1 (environment, read at bvr_create): about one ray in 1024 of the last render was traced again in the
+     * kernel with the reference's own traversal order and boxes (raytrace.wgsl:313-346); a different closest hit counts
+     * as a mismatch.  Both stay 0 when the check is off. */
+    uint64_t selfcheck_rays;
+    uint64_t selfcheck_mismatches;
 } BvrStats;
 
 typedef struct BvrContext BvrContext;

@@ -22,6 +22,14 @@
 //   * the fullscreen-triangle uv of pixel (x,y) is ((x+0.5)/W, (y+0.5)/H) in f32, (0,0) top-left;
 //   * `a || b` short-circuits (WGSL spec) at raytrace.wgsl:269;
 //   * textureSample of the raster colour / depth at a pixel centre returns that texel.
+//
+// SENSITIVITY VARIANTS (tools/oracle_sensitivity.py; never used as the checker): what a real WGSL toolchain may
+// legally do differently.  Each macro switches ONE convention; the tool reports how far the image moves.
+//   BVRO_VAR_POW_EXP2LOG2   pow(x, 5) = exp2(5 * log2(x)) (how SPIR-V / MSL back ends usually lower pow)
+//   BVRO_VAR_RSQRT          normalize(v) = v * inversesqrt(dot(v, v))
+//   BVRO_VAR_NAN_MINMAX     min / max propagate a NaN operand (the slab test at raytrace.wgsl:390-393)
+//   BVRO_VAR_EAGER_OR       `||` evaluates both sides (older naga): one more RNG draw when cannot_refract
+//   (FMA contraction is a compiler flag: -ffp-contract=fast -mfma)
 
 #include <cmath>
 #include <cstdio>
@@ -55,7 +63,18 @@ inline float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 inline V3 cross(V3 a, V3 b) {
     return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
+#ifdef BVRO_VAR_RSQRT
+inline V3 normalize(V3 a) { return a * (1.0f / std::sqrt(dot(a, a))); }
+#else
 inline V3 normalize(V3 a) { return a / std::sqrt(dot(a, a)); }
+#endif
+#ifdef BVRO_VAR_NAN_MINMAX
+inline float wmin(float a, float b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
+inline float wmax(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
+#else
+inline float wmin(float a, float b) { return fminf(a, b); }
+inline float wmax(float a, float b) { return fmaxf(a, b); }
+#endif
 inline V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
 
 struct Counters {
@@ -139,10 +158,10 @@ inline float ray_bounding_dst(const Ray& ray, V3 box_min, V3 box_max) {
     V3 inv = v3(1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z);
     V3 t_min = (box_min - ray.origin) * inv;
     V3 t_max = (box_max - ray.origin) * inv;
-    V3 t1 = v3(fminf(t_min.x, t_max.x), fminf(t_min.y, t_max.y), fminf(t_min.z, t_max.z));
-    V3 t2 = v3(fmaxf(t_min.x, t_max.x), fmaxf(t_min.y, t_max.y), fmaxf(t_min.z, t_max.z));
-    float t_near = fmaxf(fmaxf(t1.x, t1.y), t1.z);
-    float t_far = fminf(fminf(t2.x, t2.y), t2.z);
+    V3 t1 = v3(wmin(t_min.x, t_max.x), wmin(t_min.y, t_max.y), wmin(t_min.z, t_max.z));
+    V3 t2 = v3(wmax(t_min.x, t_max.x), wmax(t_min.y, t_max.y), wmax(t_min.z, t_max.z));
+    float t_near = wmax(wmax(t1.x, t1.y), t1.z);
+    float t_far = wmin(wmin(t2.x, t2.y), t2.z);
     bool hit = t_far >= t_near && t_far > 0.0f;
     return hit ? (t_near > 0.0f ? t_near : 0.0f) : INF;
 }
@@ -285,8 +304,12 @@ inline float reflectance(float cosine, float refraction_index) {
     float r0 = (1.0f - refraction_index) / (1.0f + refraction_index);
     r0 = r0 * r0;
     float x = 1.0f - cosine;
+#ifdef BVRO_VAR_POW_EXP2LOG2
+    float x5 = std::exp2(5.0f * std::log2(x));
+#else
     float x2 = x * x;
     float x5 = (x2 * x2) * x;
+#endif
     return r0 + (1.0f - r0) * x5;
 }
 
@@ -315,7 +338,12 @@ inline bool scatter(const Scene& s, Ray& scattered, V3& attenuation, const HitIn
             float sin_theta = std::sqrt(1.0f - cos_theta * cos_theta);
             bool cannot_refract = ri * sin_theta > 1.0f;
             V3 direction;
+#ifdef BVRO_VAR_EAGER_OR
+            const bool schlick = reflectance(cos_theta, ri) > rng_next_float(state, c);
+            if (cannot_refract | schlick) {
+#else
             if (cannot_refract || reflectance(cos_theta, ri) > rng_next_float(state, c)) {
+#endif
                 direction = reflect(unit_direction, hit.normal);
             } else {
                 direction = refract(unit_direction, hit.normal, ri);
@@ -416,6 +444,41 @@ float bvro_hit_sphere(const BvrModel* m, const float* origin, const float* dir) 
 }
 float bvro_ray_bounding_dst(const float* origin, const float* dir, const float* bmin, const float* bmax) {
     return ray_bounding_dst(Ray{ld3(origin), ld3(dir)}, ld3(bmin), ld3(bmax));
+}
+
+// ---- single functions of the shader, exposed for the known-answer tests (tests/test_oracle_kat.py) ----
+// raytrace.wgsl:400-416, 364-369
+void bvro_reflect(const float* v, const float* n, float* out) { V3 r = reflect(ld3(v), ld3(n)); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+void bvro_refract(const float* v, const float* n, float ratio, float* out) { V3 r = refract(ld3(v), ld3(n), ratio); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+float bvro_reflectance(float cosine, float ri) { return reflectance(cosine, ri); }
+void bvro_background_gradient(const float* dir, float* out) {
+    V3 r = background_gradient(Ray{v3(0, 0, 0), ld3(dir)});
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+// raytrace.wgsl:139-156: camera ray of the pixel whose uv is (u, v); *state advances by the two jitter draws
+void bvro_random_ray_from_uv(const BvrCamera* camera, const BvrWindow* window, float u, float v, uint32_t* state,
+                             float* origin, float* dir) {
+    Scene s{};
+    s.camera = *camera; s.window = *window; s.tan_half_fov = bvro_tan_half_fov(camera->fov);
+    Counters c;
+    Ray r = random_ray_from_uv(s, u, v, *state, c);
+    origin[0] = r.origin.x; origin[1] = r.origin.y; origin[2] = r.origin.z;
+    dir[0] = r.direction.x; dir[1] = r.direction.y; dir[2] = r.direction.z;
+}
+// raytrace.wgsl:231-299: one scatter event on `material` for a ray of direction ray_dir that hit at hit_pos with
+// hit_normal / front_face.  Returns absorbed; *state advances by every draw taken.
+int bvro_scatter(const BvrMaterial* material, const float* ray_dir, const float* hit_pos, const float* hit_normal,
+                 int front_face, uint32_t* state, float* out_dir, float* out_attenuation) {
+    Scene s{};
+    s.materials = material; s.n_materials = 1;
+    Counters c;
+    Ray ray{v3(0, 0, 0), ld3(ray_dir)};
+    HitInfo hit{1.0f, ld3(hit_pos), ld3(hit_normal), 0u, front_face != 0, 0u};
+    V3 att = v3(0, 0, 0);
+    const bool absorbed = scatter(s, ray, att, hit, *state, c);
+    out_dir[0] = ray.direction.x; out_dir[1] = ray.direction.y; out_dir[2] = ray.direction.z;
+    out_attenuation[0] = att.x; out_attenuation[1] = att.y; out_attenuation[2] = att.z;
+    return absorbed ? 1 : 0;
 }
 
 // One `fragment` invocation per pixel (raytrace.wgsl:93-123) for rows [y0, y1).

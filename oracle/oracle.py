@@ -86,6 +86,18 @@ lib.bvro_render.argtypes = [_vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _
 lib.bvro_store_srgb8.restype = None
 lib.bvro_store_srgb8.argtypes = [_vp, C.c_size_t, _vp]
 lib.bvro_max_threads.restype = C.c_int
+lib.bvro_reflect.restype = None
+lib.bvro_reflect.argtypes = [_vp, _vp, _vp]
+lib.bvro_refract.restype = None
+lib.bvro_refract.argtypes = [_vp, _vp, C.c_float, _vp]
+lib.bvro_reflectance.restype = C.c_float
+lib.bvro_reflectance.argtypes = [C.c_float, C.c_float]
+lib.bvro_background_gradient.restype = None
+lib.bvro_background_gradient.argtypes = [_vp, _vp]
+lib.bvro_random_ray_from_uv.restype = None
+lib.bvro_random_ray_from_uv.argtypes = [_vp, _vp, C.c_float, C.c_float, C.POINTER(C.c_uint32), _vp, _vp]
+lib.bvro_scatter.restype = C.c_int
+lib.bvro_scatter.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_uint32), _vp, _vp]
 
 
 def _ptr(a):
@@ -141,3 +153,49 @@ def store_srgb8(rgba):
 
 def max_threads():
     return lib.bvro_max_threads()
+
+
+# ---- single shader functions (known-answer tests) ----
+def _f3(v):
+    return np.ascontiguousarray(v, np.float32)
+
+
+def reflect(v, n):
+    out = np.zeros(3, np.float32)
+    lib.bvro_reflect(_ptr(_f3(v)), _ptr(_f3(n)), _ptr(out))
+    return out
+
+
+def refract(v, n, ratio):
+    out = np.zeros(3, np.float32)
+    lib.bvro_refract(_ptr(_f3(v)), _ptr(_f3(n)), float(ratio), _ptr(out))
+    return out
+
+
+def reflectance(cosine, ri):
+    return np.float32(lib.bvro_reflectance(float(cosine), float(ri)))
+
+
+def background_gradient(direction):
+    out = np.zeros(3, np.float32)
+    lib.bvro_background_gradient(_ptr(_f3(direction)), _ptr(out))
+    return out
+
+
+def random_ray_from_uv(camera, window, u, v, state):
+    """Returns (origin, direction, state after the two jitter draws)."""
+    st = C.c_uint32(int(state))
+    o, d = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    lib.bvro_random_ray_from_uv(C.addressof(camera), C.addressof(window), float(u), float(v), C.byref(st), _ptr(o), _ptr(d))
+    return o, d, st.value
+
+
+def scatter(material, ray_dir, hit_pos, hit_normal, front_face, state):
+    """material: one record of the 32-byte material layout.  Returns (absorbed, direction, attenuation, state)."""
+    material = np.ascontiguousarray(material)
+    assert material.dtype.itemsize == 32
+    st = C.c_uint32(int(state))
+    d, a = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    absorbed = lib.bvro_scatter(_ptr(material), _ptr(_f3(ray_dir)), _ptr(_f3(hit_pos)), _ptr(_f3(hit_normal)), int(bool(front_face)),
+                                C.byref(st), _ptr(d), _ptr(a))
+    return bool(absorbed), d, a, st.value

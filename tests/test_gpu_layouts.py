@@ -11,7 +11,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-KNOBS = ("BVR_NO_BVH4", "BVR_NO_Q16", "BVR_NO_TIGHT", "BVR_MK_V1", "BVR_MK_THREADS", "BVR_GPU_VALIDATE", "BVR_NO_TOP")
+KNOBS = ("BVR_NO_BVH4", "BVR_NO_Q16", "BVR_NO_TIGHT", "BVR_MK_V1", "BVR_MK_THREADS", "BVR_GPU_VALIDATE", "BVR_NO_BOTH", "BVR_SELFCHECK")
 
 
 def bits(a):
@@ -42,7 +42,7 @@ def check(got, want, cnt, stats, tag):
     assert stats["rays"] == cnt["rays"], tag
 
 
-SMALL = [dict(), dict(BVR_NO_BVH4=1), dict(BVR_NO_TIGHT=1), dict(BVR_MK_V1=1),
+SMALL = [dict(), dict(BVR_NO_BVH4=1), dict(BVR_NO_TIGHT=1), dict(BVR_NO_BOTH=1), dict(BVR_MK_V1=1),
          dict(BVR_MK_THREADS=512), dict(BVR_NO_BVH4=1, BVR_MK_THREADS=768)]
 
 
@@ -213,3 +213,28 @@ def test_dirty_range_upload_of_a_big_scene(bvr, oracle, knobs):
     want, cnt = oracle.render(models, mats, nodes, cam, bvr.make_level(3), win, W)
     check(got, want, cnt, c.stats(), "dirty big scene")
     c.close()
+
+
+def test_selfcheck_mode_retraces_sampled_rays_in_reference_order(bvr, oracle, ctx, rtiow, knobs):
+    """BVR_SELFCHECK=1: about one finished ray in 1024 is traced again, in the kernel, with the reference's own traversal
+    order and boxes; the culling shortcuts (tight boxes, 16-bit grid, FMA slab test) must never change a closest hit."""
+    W, H = 480, 270
+    cam = bvr.make_camera(position=(13, 2, 3), target=(0, 0, 0), fov=float(np.deg2rad(20)), aspect=W / H, sample_count=8, bounces=10)
+    win = bvr.make_window(0.37, H)
+    big = bvr.Scene.random(3, 30000, 62.0, 0.05, 0.25)
+    bcam = bvr.make_camera(position=(0, 0, 42), target=(0, 0, 0), aspect=W / H, sample_count=4, bounces=8)
+    for scene, c, env in ((rtiow, cam, dict()), (rtiow, cam, dict(BVR_NO_BOTH=1)), (rtiow, cam, dict(BVR_NO_TIGHT=1)),
+                          (big, bcam, dict()), (big, bcam, dict(BVR_NO_BVH4=1))):
+        knobs(**env)
+        ctx.upload_scene(scene.models, scene.materials, scene.nodes)
+        off = ctx.render(c, 3, win, bvr.make_options(W, kernel=1))
+        st = ctx.stats()
+        assert st["selfcheck_rays"] == 0 and st["selfcheck_mismatches"] == 0
+        knobs(BVR_SELFCHECK=1, **env)
+        on = ctx.render(c, 3, win, bvr.make_options(W, kernel=1))
+        st1 = ctx.stats()
+        assert st1["rays"] == st["rays"]
+        assert st["rays"] / 4096 < st1["selfcheck_rays"] < st["rays"] / 256, (env, st1)
+        assert st1["selfcheck_mismatches"] == 0, (env, st1)
+        for k in off:
+            assert np.array_equal(bits(on[k]), bits(off[k])), (env, k)

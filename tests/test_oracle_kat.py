@@ -252,3 +252,268 @@ def test_exact_ties_go_to_the_leaf_popped_first(bvr, oracle):
     assert (brute["primary_id"][hit] == 0).all()       # buffer order: first model first
     ranks, _ = bvr.traversal_ranks(nodes, 2)
     assert list(ranks) == [1, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Per-function known answers for the path logic (raytrace.wgsl:139-299, 364-369, 400-416), derived here statement by
+# statement in scalar numpy float32 — one IEEE operation per Python operator, in the WGSL's order.
+# ---------------------------------------------------------------------------------------------------------------------
+f = np.float32
+
+
+def _dot(a, b):
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]
+
+
+def _vec(*xs):
+    return np.array(xs, np.float32)
+
+
+def _normalize(v):
+    return v / np.sqrt(_dot(v, v))
+
+
+def _next_float(state):
+    state = py_rng_next(state)
+    return f(state) / f(4294967296.0), state
+
+
+def _ball(state):
+    """random.wgsl:17-26 on Python integers / f32 scalars; returns (p, state, iterations)."""
+    it = 0
+    while True:
+        it += 1
+        x, state = _next_float(state)
+        y, state = _next_float(state)
+        z, state = _next_float(state)
+        p = f(2.0) * _vec(x, y, z) - f(1.0)
+        if _dot(p, p) <= f(1.0):
+            return p, state, it
+
+
+def _material(bvr, **kw):
+    m = np.zeros(1, bvr.MATERIAL_DTYPE)
+    m["base_color"] = (0.8, 0.6, 0.2)
+    m["roughness"], m["ior"] = 0.5, 1.5
+    for k, v in kw.items():
+        m[k] = v
+    return m
+
+
+def test_reflect_refract_reflectance_background(oracle):
+    v = _normalize(_vec(0.3, -0.8, 0.52))
+    n = _normalize(_vec(0.1, 1.0, -0.2))
+    # reflect, raytrace.wgsl:400-402:  v - 2 * dot(v, n) * n
+    want = v - (f(2.0) * _dot(v, n)) * n
+    assert np.array_equal(oracle.reflect(v, n).view(np.uint32), want.view(np.uint32))
+    # refract, raytrace.wgsl:404-409
+    for ratio in (f(1.0) / f(1.5), f(1.5), f(0.7)):
+        cos_theta = min(_dot(-v, n), f(1.0))
+        perp = ratio * (v + cos_theta * n)
+        parallel = -np.sqrt(np.abs(f(1.0) - _dot(perp, perp))) * n
+        want = perp + parallel
+        assert np.array_equal(oracle.refract(v, n, ratio).view(np.uint32), want.view(np.uint32))
+    # reflectance, raytrace.wgsl:411-416 with pow(x, 5) = ((x x)(x x)) x
+    for cosine, ri in ((f(0.0), f(1.5)), (f(0.37), f(1.0) / f(1.5)), (f(1.0), f(2.4)), (f(0.9), f(0.7))):
+        r0 = (f(1.0) - ri) / (f(1.0) + ri)
+        r0 = r0 * r0
+        x = f(1.0) - cosine
+        want = r0 + (f(1.0) - r0) * (((x * x) * (x * x)) * x)
+        assert oracle.reflectance(cosine, ri) == want
+    assert oracle.reflectance(1.0, 1.5) == (f(-0.5) / f(2.5)) * (f(-0.5) / f(2.5))   # head-on glass: r0 = ((1 - 1.5) / 2.5)^2 = 0.04
+    # background_gradient, raytrace.wgsl:364-369
+    for d in (_vec(0, 1, 0), _vec(0, -3, 0), _vec(1.0, 0.25, -2.0)):
+        unit = _normalize(d)
+        a = f(0.5) * (unit[1] + f(1.0))
+        want = (f(1.0) - a) * _vec(1, 1, 1) + a * _vec(0.5, 0.7, 1.0)
+        assert np.array_equal(oracle.background_gradient(d).view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(oracle.background_gradient(_vec(0, 1, 0)), _vec(0.5, 0.7, 1.0))     # straight up: sky blue
+    assert np.array_equal(oracle.background_gradient(_vec(0, -1, 0)), _vec(1, 1, 1))          # straight down: white
+
+
+def test_random_ray_from_uv(bvr, oracle):
+    """raytrace.wgsl:139-156: two draws (x then y), jitter of one pixel, ray through the jittered ndc point."""
+    W, H = 1280, 720
+    cam = bvr.make_camera(position=(13, 2, 3), target=(0, 0, 0), fov=float(np.deg2rad(20)), aspect=W / H)
+    win = bvr.make_window(0.5, H)
+    direction, up, position = _vec(*cam.direction), _vec(*cam.up), _vec(*cam.position)
+    for (x, y, state) in ((0, 0, 17), (639, 359, 15794417), (1279, 719, 63246312), (100, 650, 0xDEADBEEF)):
+        u, v = (f(x) + f(0.5)) / f(W), (f(y) + f(0.5)) / f(H)
+        r1, s1 = _next_float(state)
+        r2, s2 = _next_float(s1)
+        rand_square = (r1 - f(0.5), r2 - f(0.5))
+        height = f(H)
+        width = f(H) * f(cam.aspect)
+        delta_u = (f(1.0) / width) * rand_square[0]
+        delta_v = (f(1.0) / height) * rand_square[1]
+        ndc_x = (u * f(2.0) - f(1.0)) + delta_u
+        ndc_y = (f(1.0) - v * f(2.0)) + delta_v
+        right = _vec(direction[1] * up[2] - direction[2] * up[1], direction[2] * up[0] - direction[0] * up[2],
+                     direction[0] * up[1] - direction[1] * up[0])
+        scale = f(np.tan(np.float64(f(cam.fov) * f(0.5))))
+        want = _normalize((direction + (ndc_x * f(cam.aspect) * scale) * right) + (ndc_y * scale) * up)
+        o, d, s_out = oracle.random_ray_from_uv(cam, win, u, v, state)
+        assert s_out == s2
+        assert np.array_equal(o, position) and np.array_equal(d.view(np.uint32), want.view(np.uint32))
+        assert abs(float(_dot(d, d)) - 1.0) < 1e-6
+
+
+def test_scatter_metal_branch(bvr, oracle):
+    """raytrace.wgsl:234-246: u1 < metallic; direction = normalize(reflect(d, n)) + roughness * ball; the ball is drawn
+    even when roughness is 0; absorbed iff the fuzzed direction points below the surface."""
+    n = _vec(0, 1, 0)
+    hit = _vec(1.5, 0.25, -2.0)
+    d_in = _vec(0.6, -0.3, 0.2)                                   # not normalised: the reference never normalises bounces
+    seen = set()
+    for state in (1, 2, 3, 12345, 99, 1000, 31337, 5):
+        for rough in (0.0, 0.5, 1.0):
+            m = _material(bvr, metallic=1.0, roughness=rough)
+            u1, s = _next_float(state)
+            assert u1 < f(1.0) or u1 == f(1.0)
+            if not (u1 < f(1.0)):
+                continue
+            b, s, _ = _ball(s)
+            want = _normalize(d_in - (f(2.0) * _dot(d_in, n)) * n) + f(rough) * b
+            absorbed, d, att, s_out = oracle.scatter(m, d_in, hit, n, True, state)
+            assert s_out == s and np.array_equal(d.view(np.uint32), want.view(np.uint32))
+            assert np.array_equal(att, m["base_color"][0])
+            assert absorbed == bool(_dot(want, n) < f(0.0))
+            seen.add(absorbed)
+    # grazing incidence + full fuzz: some rays end up below the surface
+    d_graze = _vec(1.0, -0.02, 0.0)
+    for state in range(40):
+        m = _material(bvr, metallic=1.0, roughness=1.0)
+        absorbed, d, _, _ = oracle.scatter(m, d_graze, hit, n, True, state)
+        assert absorbed == bool(_dot(d, n) < f(0.0))
+        seen.add(absorbed)
+    assert seen == {True, False}
+
+
+def test_scatter_diffuse_branch(bvr, oracle):
+    """raytrace.wgsl:283-298: u1 >= metallic, u2 >= transmission; direction = normal + ball1 + roughness * ball2 (drawn
+    in that order), unnormalised; absorbed iff it points below the surface."""
+    n = _normalize(_vec(0.2, 0.9, -0.3))
+    hit = _vec(-4.0, 0.2, 1.0)
+    d_in = _vec(0.1, -1.0, 0.3)
+    seen = set()
+    for state in range(1, 300):
+        rough = (0.5, 1.0)[state % 2]
+        m = _material(bvr, metallic=0.0, specular_transmission=0.0, roughness=rough)
+        u1, s = _next_float(state)
+        u2, s = _next_float(s)
+        b1, s, _ = _ball(s)
+        b2, s, _ = _ball(s)
+        want = (n + b1) + f(rough) * b2
+        absorbed, d, att, s_out = oracle.scatter(m, d_in, hit, n, True, state)
+        assert s_out == s
+        assert np.array_equal(d.view(np.uint32), want.view(np.uint32)) and np.array_equal(att, m["base_color"][0])
+        assert absorbed == bool(_dot(want, n) < f(0.0))
+        seen.add(absorbed)
+    assert seen == {True, False}       # |ball1| + roughness |ball2| can exceed 1: a few per cent of diffuse bounces are absorbed
+    # fractional metallic: the branch is picked by the first draw alone
+    m = _material(bvr, metallic=0.3)
+    kinds = set()
+    for state in range(1, 40):
+        u1, _ = _next_float(state)
+        _, d, att, s_out = oracle.scatter(m, d_in, hit, n, True, state)
+        s = py_rng_next(state)
+        if u1 < f(0.3):
+            b, s, _ = _ball(s)
+            kinds.add("metal")
+        else:
+            s = py_rng_next(s)
+            _, s, _ = _ball(s)
+            _, s, _ = _ball(s)
+            kinds.add("diffuse")
+        assert s_out == s
+    assert kinds == {"metal", "diffuse"}
+
+
+def test_scatter_glass_branch(bvr, oracle):
+    """raytrace.wgsl:248-282: ri = 1/ior on a front face, ior otherwise; total internal reflection takes NO draw
+    (`||` short-circuits), otherwise one draw against Schlick; attenuation 1, never absorbed."""
+    n = _vec(0, 0, 1)
+    hit = _vec(0.5, 0.5, 3.0)
+    taken = set()
+    for ior, front, d_in in ((1.5, True, _vec(0.2, 0.1, -1.0)), (1.5, True, _vec(3.0, 0.0, -0.2)),
+                             (1.5, False, _vec(0.9, 0.0, -0.3)),          # back face, ri = 1.5: total internal reflection
+                             (0.7, True, _vec(1.0, 0.2, -0.25)),          # ior < 1 on a front face: ri = 1/0.7 > 1
+                             (2.4, True, _vec(0.0, 0.0, -2.0))):
+        for state in (7, 8, 9, 10, 11, 12, 4242, 777):
+            m = _material(bvr, metallic=0.0, specular_transmission=1.0, ior=ior)
+            u1, s = _next_float(state)
+            u2, s = _next_float(s)
+            if not (u2 < f(1.0)):
+                continue
+            ri = f(1.0) / f(ior) if front else f(ior)
+            unit = _normalize(d_in)
+            cos_theta = min(_dot(-unit, n), f(1.0))
+            sin_theta = np.sqrt(f(1.0) - cos_theta * cos_theta)
+            cannot = bool(ri * sin_theta > f(1.0))
+            if cannot:
+                reflects = True
+                taken.add("tir")
+            else:
+                r0 = (f(1.0) - ri) / (f(1.0) + ri)
+                r0 = r0 * r0
+                x = f(1.0) - cos_theta
+                schlick = r0 + (f(1.0) - r0) * (((x * x) * (x * x)) * x)
+                u3, s = _next_float(s)
+                reflects = bool(schlick > u3)
+                taken.add("reflect" if reflects else "refract")
+            if reflects:
+                want = unit - (f(2.0) * _dot(unit, n)) * n
+            else:
+                ct = min(_dot(-unit, n), f(1.0))
+                perp = ri * (unit + ct * n)
+                want = perp + (-np.sqrt(np.abs(f(1.0) - _dot(perp, perp)))) * n
+            absorbed, d, att, s_out = oracle.scatter(m, d_in, hit, n, front, state)
+            assert not absorbed and np.array_equal(att, _vec(1, 1, 1))
+            assert s_out == s, (ior, front, state)
+            assert np.array_equal(d.view(np.uint32), want.view(np.uint32))
+    assert taken == {"tir", "reflect", "refract"}
+
+
+def test_raytrace_exits(bvr, oracle):
+    """The three ways out of raytrace's loop (raytrace.wgsl:188-224), on one-sphere scenes through the whole fragment:
+    miss -> gamma-encoded sky, depth = fallback; absorbed -> black; loop exhausted (bounce_count + 1 hits) -> black."""
+    def scene(radius, **mat):
+        models = np.zeros(1, bvr.MODEL_DTYPE)
+        models["position"], models["radius"], models["material_id"] = (0, 0, -5), radius, 0
+        mats = _material(bvr, **mat)
+        nodes = np.zeros(1, bvr.BVH_NODE_DTYPE)
+        nodes["bounds_min"], nodes["bounds_max"] = models["position"][0] - (radius + 0.1), models["position"][0] + (radius + 0.1)
+        nodes["index"], nodes["model_count"] = 0, 1
+        return models, mats, nodes
+    W = H = 9
+    far = 1000.0
+    # miss: a pixel in the corner never meets the small sphere; level 1 falls back to far + 10, the others to far - 1
+    models, mats, nodes = scene(0.5)
+    for level, fallback in ((1, f(far) + f(10.0)), (2, f(far) - f(1.0)), (3, f(far) - f(1.0))):
+        cam = bvr.make_camera(position=(0, 0, 0), target=(0, 0, -1), aspect=1.0, sample_count=1, bounces=3, far=far)
+        raster, depth = np.zeros((H, W, 4), np.float32), np.zeros((H, W), np.float32)
+        planes, _ = oracle.render(models, mats, nodes, cam, bvr.make_level(level), bvr.make_window(0.4, H), W, raster, depth)
+        assert planes["primary_id"][0, 0] == 0xFFFFFFFF and planes["rt_depth"][0, 0] == fallback
+        if level == 3:
+            # the colour of a miss is sqrt(1 * sky(direction)) per channel: recompute it from the camera ray
+            u, v = (f(0) + f(0.5)) / f(W), (f(0) + f(0.5)) / f(H)
+            seed = np_pixel_seed(0.4, 0, 0, W, H)
+            _, d, _ = oracle.random_ray_from_uv(cam, bvr.make_window(0.4, H), u, v, seed)
+            sky = oracle.background_gradient(d)
+            assert np.array_equal(planes["rgba"][0, 0, :3].view(np.uint32), np.sqrt(sky).view(np.uint32))
+            assert planes["rgba"][0, 0, 3] == 1.0
+    # loop exhausted: camera INSIDE a big mirror-less glass... simpler: bounces = 0 and a hit -> one scatter, then black
+    models, mats, nodes = scene(2.0)
+    cam = bvr.make_camera(position=(0, 0, 0), target=(0, 0, -1), aspect=1.0, sample_count=3, bounces=0)
+    planes, cnt = oracle.render(models, mats, nodes, cam, bvr.make_level(3), bvr.make_window(0.4, H), W)
+    c = H // 2
+    assert planes["primary_id"][c, c] == 0 and np.array_equal(planes["rgba"][c, c], _vec(0, 0, 0, 1))
+    assert np.isclose(planes["rt_depth"][c, c], 3.0, atol=0.01) and 3.0 <= planes["primary_depth"][c, c] < 3.01   # jittered centre pixel
+    # absorbed: a fully fuzzed metal seen at grazing incidence absorbs some samples -> their contribution is 0, the
+    # others see sky through the tinted reflection; with one sample per pixel a pixel is either exactly black or not
+    models, mats, nodes = scene(2.0, metallic=1.0, roughness=1.0)
+    cam = bvr.make_camera(position=(0, 0, 0), target=(0, 0, -1), aspect=1.0, sample_count=1, bounces=50)
+    planes, cnt = oracle.render(models, mats, nodes, cam, bvr.make_level(3), bvr.make_window(0.9, 64), 64)
+    on_sphere = planes["primary_id"] == 0
+    black = (planes["rgba"][..., :3] == 0).all(axis=2)
+    assert (black & on_sphere).sum() > 0 and (~black & on_sphere).sum() > 0 and not (black & ~on_sphere).any()
