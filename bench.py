@@ -520,10 +520,27 @@ def run_leg(d, bvr, capi, key, args, peaks, steps, warmup, with_cpu, gpu_bvh=Fal
     return line
 
 
-def run_c5(args, frames, gpu_bvh):
+def dirty_model_ranges(capi, models, prev_models, bridge=16):
+    """Runs of changed 32-byte model records as (array, first, count), bridged over gaps of up to `bridge` clean ones
+    (one copy per run); numpy only — this is what a caller's change detection costs per frame."""
+    changed = (models.view(np.uint8).reshape(-1, 32) != prev_models.view(np.uint8).reshape(-1, 32)).any(axis=1)
+    dm = np.flatnonzero(changed)
+    if not len(dm):
+        return []
+    cut = np.flatnonzero(np.diff(dm) > bridge)
+    starts = np.concatenate(([dm[0]], dm[cut + 1]))
+    ends = np.concatenate((dm[cut], [dm[-1]]))
+    return [(capi.ARRAY_MODELS, int(a), int(b - a + 1)) for a, b in zip(starts, ends)]
+
+
+def run_c5(args, frames, mode):
     """BASELINE.json configs[4]: animated 10k-sphere scene, per-frame BVH rebuild, dirty-range upload, render at the demo
     defaults (4 spp, 4 bounces, level FallbackRaytraced) with the fused depth composite against a synthetic raster
-    colour/depth; host buffers in and out every frame.  Reports the per-frame split."""
+    colour/depth; host buffers in and out every frame.  mode:
+      "host"      per-frame host PLOC build (the reference's flow, extract.rs:316-321) + dirty-range upload + bvr_render
+      "gpu"       models only travel, bvr_upload_scene_gpu_bvh builds the tree on the GPU, bvr_render
+      "pipelined" as "gpu" with two contexts: frame f renders asynchronously (bvr_render_async) in one while frame f+1's
+                  models are uploaded and its tree is built in the other; a frame is complete when its pixels are in host memory"""
     import torch
 
     import bevyray_b200 as bvr
@@ -531,83 +548,89 @@ def run_c5(args, frames, gpu_bvh):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — bevyray_b200 has no CPU fallback")
     W, H = 1280, 720
+    gpu_bvh = mode != "host"
     scene = bvr.Scene.random(11, 10000, 43.0, 0.05, 0.25)
     cam = bvr.make_camera(position=(0.0, 0.0, 40.0), target=(0.0, 0.0, 0.0), aspect=W / H, sample_count=4, bounces=4)
-    ctx = bvr.Context(0)
+    n_ctx = 2 if mode == "pipelined" else 1
+    ctxs = [bvr.Context(0) for _ in range(n_ctx)]
     rs = np.random.RandomState(0)
     raster = torch.from_numpy(rs.rand(H, W, 4).astype(np.float32)).pin_memory().numpy()
     depth = torch.from_numpy((rs.rand(H, W) * 0.004).astype(np.float32)).pin_memory().numpy()
-    out = {"rgba": torch.empty((H, W, 4), dtype=torch.float32).pin_memory().numpy()}
+    outs = [{"rgba": torch.empty((H, W, 4), dtype=torch.float32).pin_memory().numpy()} for _ in range(n_ctx)]
     opts = bvr.make_options(W)
-    ctx.upload_scene(scene.models, scene.materials, scene.nodes)
-    prev_models, prev_nodes = scene.models.copy(), scene.nodes.copy()
+    prevs = []
+    for c in ctxs:
+        if gpu_bvh:
+            c.upload_scene_gpu_bvh(scene.models, scene.materials)
+        else:
+            c.upload_scene(scene.models, scene.materials, scene.nodes)
+        prevs.append(scene.models.copy())
+    prev_nodes = scene.nodes.copy()
     t_build = t_upload = t_render = gpu_build_ms = 0.0
     rays = h2d = 0
     sampler = ClockSampler(0)
     sampler.start()
     t_all0 = time.perf_counter()
     for f in range(frames):
+        k = f % n_ctx
+        ctx = ctxs[k]
         t0 = time.perf_counter()
-        scene.animate(f + 1)                                  # closed-form motion + PLOC rebuild (host)
+        scene.animate(f + 1, rebuild_bvh=not gpu_bvh)        # closed-form motion (+ host PLOC rebuild in "host" mode)
         t1 = time.perf_counter()
-        m, n = scene.models, scene.nodes
-        # dirty model ranges: runs of changed models, bridged over gaps < 16 (one copy per run)
-        dm = np.nonzero((m.view(np.uint8).reshape(-1, 32) != prev_models.view(np.uint8).reshape(-1, 32)).any(axis=1))[0]
-        ranges = []
-        if len(dm):
-            start = prev = int(dm[0])
-            for i in dm[1:]:
-                i = int(i)
-                if i - prev > 16:
-                    ranges.append((capi.ARRAY_MODELS, start, prev - start + 1))
-                    start = i
-                prev = i
-            ranges.append((capi.ARRAY_MODELS, start, prev - start + 1))
+        m = scene.models
+        if mode == "pipelined":
+            ctx.sync()                                        # frame f-2 of this context is complete: its buffers are free
+            rays += ctx.stats()["rays"] if f >= n_ctx else 0
+        ranges = dirty_model_ranges(capi, m, prevs[k])
         win = bvr.make_window((0.37 + 0.013 * f) % 1.0, H)
+        st0 = ctx.stats()["h2d_bytes"]
         if gpu_bvh:
-            # models only travel; the library rebuilds the BVH on the GPU (bvr_upload_scene_gpu_bvh).  The host
-            # PLOC time inside scene.animate() is then not part of the frame: it is subtracted below.
-            st0 = ctx.stats()["h2d_bytes"]
-            ctx.upload_scene_gpu_bvh(m, scene.materials, ranges if f > 0 else None)
+            ctx.upload_scene_gpu_bvh(m, scene.materials, ranges)
             st1 = ctx.stats()
-            h2d += st1["h2d_bytes"] - st0
             gpu_build_ms += st1["last_upload_ms"]
-            prev_models = m.copy()
+            h2d += st1["h2d_bytes"] - st0
         else:
-            # ... plus the span of changed BVH nodes
-            dn = np.nonzero((n.view(np.uint8).reshape(-1, 48) != prev_nodes.view(np.uint8).reshape(-1, 48)).any(axis=1))[0]
+            n = scene.nodes
+            dn = np.flatnonzero((n.view(np.uint8).reshape(-1, 48) != prev_nodes.view(np.uint8).reshape(-1, 48)).any(axis=1))
             if len(dn):
-                ranges.append((capi.ARRAY_BVH_NODES, int(dn.min()), int(dn.max() - dn.min() + 1)))
-            st0 = ctx.stats()["h2d_bytes"]
+                ranges.append((capi.ARRAY_BVH_NODES, int(dn[0]), int(dn[-1] - dn[0] + 1)))
             ctx.upload_scene(m, scene.materials, n, ranges)
             h2d += ctx.stats()["h2d_bytes"] - st0
-            prev_models, prev_nodes = m.copy(), n.copy()
+            prev_nodes = n.copy()
+        prevs[k] = m.copy()
         t2 = time.perf_counter()
-        ctx.render(cam, 2, win, opts, raster, depth, want=("rgba",), out=out)
+        ctx.render(cam, 2, win, opts, raster, depth, want=("rgba",), out=outs[k], asynchronous=mode == "pipelined")
         t3 = time.perf_counter()
-        rays += ctx.stats()["rays"]
+        if mode != "pipelined":
+            rays += ctx.stats()["rays"]
         t_build += t1 - t0
         t_upload += t2 - t1
         t_render += t3 - t2
+    for c in ctxs:
+        c.sync()
+        if mode == "pipelined":
+            rays += c.stats()["rays"]
     total = time.perf_counter() - t_all0
     clocks = sampler.stop()
-    if gpu_bvh:
-        total -= t_build      # host animate+PLOC is bench scaffolding in this mode (the tree comes from the GPU)
     line = {"metric": "frame ms, animated 10k spheres 1280x720 4spp 4 bounces level 2 (BVH rebuild + dirty upload + render + composite)",
             "value": total / frames * 1e3, "unit": "ms/frame", "n_gpus": 1, "steps": frames, "warmup": 0,
             "ms_per_step": total / frames * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C5 animated 10k random spheres, {frames} frames, per-frame BVH rebuild, dirty-range upload, "
-                                   "fused depth composite vs synthetic raster"},
-            "split_ms": {"host_bvh_build": 0.0 if gpu_bvh else t_build / frames * 1e3,
-                         "dirty_detect_and_upload": t_upload / frames * 1e3, "render_with_host_io": t_render / frames * 1e3},
-            "bvh": "GPU builder (bvr_upload_scene_gpu_bvh)" if gpu_bvh else "host PLOC (csrc/host/ploc.cpp)",
+            "config": {"workload": f"C5 animated 10k random spheres (every 4th moves), {frames} frames, per-frame BVH rebuild, dirty-range "
+                                   "upload, fused depth composite vs synthetic raster, host buffers in and out"},
+            "mode": {"host": "host PLOC (csrc/host/ploc.cpp) + bvr_upload_scene + bvr_render",
+                     "gpu": "bvr_upload_scene_gpu_bvh (tree built on the GPU) + bvr_render",
+                     "pipelined": "two contexts: bvr_upload_scene_gpu_bvh of frame f+1 overlaps bvr_render_async of frame f"}[mode],
+            "split_ms": {"host_animate" + ("_and_bvh_build" if not gpu_bvh else ""): t_build / frames * 1e3,
+                         "dirty_detect_and_upload": t_upload / frames * 1e3,
+                         ("render_enqueue" if mode == "pipelined" else "render_with_host_io"): t_render / frames * 1e3},
             "gpu_upload_and_build_ms": gpu_build_ms / frames if gpu_bvh else None,
             "e2e": {"value": total / frames * 1e3, "unit": "ms/frame", "h2d_bytes_per_step": int(h2d / frames + W * H * 20),
                     "d2h_bytes_per_step": W * H * 16},
             "mrays_per_s": rays / total / 1e6, "scene_h2d_bytes_per_frame": h2d / frames,
             "full_scene_bytes": int(scene.models.nbytes + scene.materials.nbytes + scene.nodes.nbytes), "clocks": clocks}
-    ctx.close()
+    for c in ctxs:
+        c.close()
     return line
 
 
@@ -631,9 +654,9 @@ def run_ours(args):
                                                   "gpu_launches", "clocks", "config", "roofline", "roofline_hbm") if k in leg}
             except Exception as e:   # a leg must never take the headline line down with it
                 extra[key] = {"error": repr(e)}
-        for name, gpu_bvh in (("c5_host_bvh", False), ("c5_gpu_bvh", True)):
+        for name, mode in (("c5_host_bvh", "host"), ("c5_gpu_bvh", "gpu"), ("c5_gpu_bvh_pipelined", "pipelined")):
             try:
-                extra[name] = run_c5(args, 60, gpu_bvh)
+                extra[name] = run_c5(args, 60, mode)
             except Exception as e:
                 extra[name] = {"error": repr(e)}
     if d.rank == 0:
@@ -650,6 +673,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--gpu-bvh", action="store_true", help="build the BVH on the GPU instead of the host PLOC")
     ap.add_argument("--frames", type=int, default=300, help="frames of the animated workload (c5)")
+    ap.add_argument("--c5-mode", default=None, choices=["host", "gpu", "pipelined"], help="c5: see run_c5")
     ap.add_argument("--kernel", default="auto", choices=["auto", "megakernel", "wavefront", "cta-wavefront"])
     ap.add_argument("--reference-order", action="store_true", help="reference traversal order (raytrace.wgsl:313-346)")
     ap.add_argument("--shard", default="samples", choices=["samples", "tiles"])
@@ -675,7 +699,7 @@ def main():
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     if args.workload == "c5":
         if int(os.environ.get("RANK", "0")) == 0:
-            print(json.dumps(run_c5(args, args.frames, args.gpu_bvh)), flush=True)
+            print(json.dumps(run_c5(args, args.frames, args.c5_mode or ("gpu" if args.gpu_bvh else "host"))), flush=True)
         return
     if args.impl == "reference":
         run_reference(args)

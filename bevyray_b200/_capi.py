@@ -111,9 +111,11 @@ SIGNATURES = {
     "bvr_reload_tuning": (_i, [_vp]),
     "bvr_upload_scene": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz]),
     "bvr_upload_scene_gpu_bvh": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "bvr_refit_scene_gpu_bvh": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp]),
     "bvr_shard_rows": (_u32, [_u32, _P(BvrRenderOptions)]),
     "bvr_scene_traversal_ranks": (_i, [_vp, _sz, _sz, _vp, _vp]),
     "bvr_render": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _P(BvrWindow), _P(BvrRenderOptions), _vp, _vp, _P(BvrOutputs)]),
+    "bvr_render_async": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _P(BvrWindow), _P(BvrRenderOptions), _vp, _vp, _P(BvrOutputs)]),
     "bvr_render_device": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _P(BvrWindow), _P(BvrRenderOptions), _vp, _vp, _P(BvrOutputs)]),
     "bvr_axpby_device": (_i, [_vp, _vp, _f, _vp, _f, _sz]),
     "bvr_composite_device": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _vp, _vp, _vp, _vp, _sz]),
@@ -126,6 +128,7 @@ SIGNATURES = {
     "bvrh_scene_random": (_vp, [_u64, _u32, _f, _f, _f]),
     "bvrh_scene_from_models": (_vp, [_vp, _sz, _vp, _sz]),
     "bvrh_scene_animate": (_i, [_vp, _u32]),
+    "bvrh_scene_animate_models": (_i, [_vp, _u32]),
     "bvrh_scene_free": (None, [_vp]),
     "bvrh_scene_n_models": (_sz, [_vp]),
     "bvrh_scene_n_materials": (_sz, [_vp]),

@@ -81,8 +81,10 @@ class Scene:
         materials = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
         return cls(lib.bvrh_scene_from_models(_ptr(models), len(models), _ptr(materials), len(materials)))
 
-    def animate(self, frame):
-        if lib.bvrh_scene_animate(self._h, frame) != 0:
+    def animate(self, frame, rebuild_bvh=True):
+        """Closed-form motion of every 4th sphere; rebuild_bvh=False leaves the (then stale) node array alone."""
+        fn = lib.bvrh_scene_animate if rebuild_bvh else lib.bvrh_scene_animate_models
+        if fn(self._h, frame) != 0:
             raise RuntimeError("bvrh_scene_animate failed")
 
     def _view(self, ptr, n, dtype):
@@ -183,8 +185,9 @@ class Context:
         self._check(lib.bvr_upload_scene(self._h, _ptr(models), len(models), _ptr(materials), len(materials),
                                          _ptr(nodes), len(nodes), rp, rn))
 
-    def upload_scene_gpu_bvh(self, models, materials, ranges=None, want_nodes=False):
-        """bvr_upload_scene_gpu_bvh: the BVH is built on the GPU; optionally returns the nodes (reference layout)."""
+    def upload_scene_gpu_bvh(self, models, materials, ranges=None, want_nodes=False, refit=False):
+        """bvr_upload_scene_gpu_bvh: the BVH is built on the GPU; optionally returns the nodes (reference layout).
+        refit=True is bvr_refit_scene_gpu_bvh: the last GPU-built topology is kept, only its boxes are refitted."""
         models = np.ascontiguousarray(models, dtype=MODEL_DTYPE)
         materials = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
         if ranges is None:
@@ -195,16 +198,19 @@ class Context:
                 arr[i].array, arr[i].first, arr[i].count = a, f, c
             rp, rn = C.cast(arr, C.c_void_p), len(ranges)
         nodes = np.zeros(max(2 * len(models) - 1, 0), dtype=BVH_NODE_DTYPE) if want_nodes else None
-        self._check(lib.bvr_upload_scene_gpu_bvh(self._h, _ptr(models), len(models), _ptr(materials), len(materials),
-                                                 rp, rn, _ptr(nodes) if want_nodes and len(nodes) else None))
+        fn = lib.bvr_refit_scene_gpu_bvh if refit else lib.bvr_upload_scene_gpu_bvh
+        self._check(fn(self._h, _ptr(models), len(models), _ptr(materials), len(materials),
+                       rp, rn, _ptr(nodes) if want_nodes and len(nodes) else None))
         return nodes
 
     def shard_rows(self, height, opts):
         return lib.bvr_shard_rows(height, C.byref(opts))
 
     def render(self, camera, level, window, opts, raster_rgba=None, raster_depth=None,
-               want=("rgba", "rt_depth", "primary_id", "primary_depth"), out=None):
-        """bvr_render with host (numpy) buffers.  Returns a dict of numpy planes of this shard's rows."""
+               want=("rgba", "rt_depth", "primary_id", "primary_depth"), out=None, asynchronous=False):
+        """bvr_render with host (numpy) buffers.  Returns a dict of numpy planes of this shard's rows.
+        asynchronous=True is bvr_render_async: every buffer must be page-locked, `out` must be given, and the planes
+        are valid after sync()."""
         rows = self.shard_rows(window.height, opts)
         w = opts.width
         shapes = {"rgba": ((rows, w, 4), np.float32), "rt_depth": ((rows, w), np.float32),
@@ -221,8 +227,9 @@ class Context:
         if raster_depth is not None:
             raster_depth = np.ascontiguousarray(raster_depth, dtype=np.float32)
         lv = level if isinstance(level, capi.BvrRaytraceLevel) else make_level(level)
-        self._check(lib.bvr_render(self._h, C.byref(camera), C.byref(lv), C.byref(window), C.byref(opts),
-                                   _ptr(raster_rgba), _ptr(raster_depth), C.byref(o)))
+        fn = lib.bvr_render_async if asynchronous else lib.bvr_render
+        self._check(fn(self._h, C.byref(camera), C.byref(lv), C.byref(window), C.byref(opts),
+                       _ptr(raster_rgba), _ptr(raster_depth), C.byref(o)))
         return res
 
     def render_device(self, camera, level, window, opts, d_raster_rgba=0, d_raster_depth=0, **device_ptrs):

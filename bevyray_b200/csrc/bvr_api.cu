@@ -54,7 +54,7 @@ struct PinnedBuffer {
 // only on request (bvr_reload_tuning); production uses the defaults.
 struct EnvTuning {
     int no_tight = 0, tight_pad = 100, no_q16 = 0, no_bvh4 = 0, gpu_validate = -1, wf_refill = 8;
-    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0, no_both = 0;
+    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0, no_both = 0, gpu_lbvh = 0;
 };
 
 struct BvrContext {
@@ -83,6 +83,8 @@ struct BvrContext {
     bool has_scene = false;
     uint32_t root_ref_host = 0;
     uint32_t tree_depth = 0;
+    float scene_extent = 0.0f;                // largest |coordinate| of the root box (guards the culling arithmetic)
+    int gpu_bvh_algorithm = 0;                // BVH_BUILD_* of the last bvr_upload_scene_gpu_bvh (its topology is in bvh_scratch)
     bool tree_is_ours = false;                // built by bvr_upload_scene_gpu_bvh: the reference never saw this tree
     uint32_t n_inner = 0;
     uint32_t max_leaf_models = 0;
@@ -91,10 +93,12 @@ struct BvrContext {
     DeviceBuffer wf_state;
     DeviceBuffer bvh_scratch;
     unsigned int* depth_host = nullptr;       // pinned
+    BvrBvhNode* root_host = nullptr;          // pinned: node 0 of a GPU-built tree
     unsigned int* wf_host_counts = nullptr;   // pinned, 8 words
     PinnedBuffer upload_staging;
     cudaEvent_t upload_done = nullptr;
     bool upload_pending = false;
+    bool pinned_src_in_flight = false;        // an upload copies straight out of a pinned caller buffer
 
     // per-frame IO for the host-buffer entry point
     DeviceBuffer in_rgba, in_depth, out_rgba, out_rt_depth, out_id, out_pdepth, out_srgb8;
@@ -153,7 +157,25 @@ EnvTuning read_env_tuning() {
     t.selfcheck = env_int("BVR_SELFCHECK", 0);
     t.no_top = env_int("BVR_NO_TOP", 0);
     t.no_both = env_int("BVR_NO_BOTH", 0);
+    t.gpu_lbvh = env_int("BVR_GPU_LBVH", 0);
     return t;
+}
+
+// The culling-only slab test computes t = c * (1/d) - o * (1/d): unlike the reference's (box - o) * (1/d) its rounding
+// error grows with |c| + |o|, about (|c| + |o|) * 2^-22 in world units.  That must stay a small fraction of the pad that
+// separates a box from its spheres — 0.01 for the tight boxes, 0.1 for the reference's — so scenes (or cameras) far from
+// the origin drop the tight boxes first and the fast slab test altogether after that.
+constexpr float BVR_TIGHT_MAX_EXTENT = 4096.0f;     // 2 * 4096 * 2^-22 = 0.002 = pad / 5
+constexpr float BVR_FAST_MAX_EXTENT = 32768.0f;     // 2 * 32768 * 2^-22 = 0.016 = pad / 6
+
+float root_extent(const BvrBvhNode& r) {
+    float m = 0.0f;
+    for (int k = 0; k < 3; k++) {
+        const float a = std::fabs(r.bounds_min[k]), b = std::fabs(r.bounds_max[k]);
+        if (!(a <= m)) m = a;     // NaN counts as "too far"
+        if (!(b <= m)) m = b;
+    }
+    return m;
 }
 
 uint32_t effective_strip_rows(const BvrRenderOptions* o) { return (o && o->strip_rows) ? o->strip_rows : 8u; }
@@ -229,6 +251,7 @@ int h2d(BvrContext* ctx, void* dst, const void* src, size_t bytes, PinnedBuffer&
     if (bytes == 0) return BVR_OK;
     if (is_pinned_host(src)) {
         BVR_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->pinned_src_in_flight = true;     // the caller's buffer is read by the DMA engine until the copy completes
     } else {
         char* st = static_cast<char*>(staging.ptr) + staging_off;
         std::memcpy(st, src, bytes);
@@ -331,6 +354,7 @@ int bvr_create(int device, BvrContext** out_ctx) {
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->ray_counter_host, 3 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->wf_host_counts, 8 * sizeof(unsigned int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->depth_host, sizeof(unsigned int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->root_host, sizeof(BvrBvhNode), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->q16_bad_host, sizeof(unsigned int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->validate_host, sizeof(ValidateOut), cudaHostAllocDefault);
     if (e == cudaSuccess) e = ctx->validate_out.ensure(sizeof(ValidateOut));
@@ -364,6 +388,7 @@ void bvr_destroy(BvrContext* ctx) {
     if (ctx->validate_host) cudaFreeHost(ctx->validate_host);
     if (ctx->q16_done) cudaEventDestroy(ctx->q16_done);
     if (ctx->depth_host) cudaFreeHost(ctx->depth_host);
+    if (ctx->root_host) cudaFreeHost(ctx->root_host);
     cudaEvent_t evs[] = {ctx->ev_render0, ctx->ev_render1, ctx->ev_upload0, ctx->ev_upload1, ctx->upload_done};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -510,6 +535,12 @@ int bvr_upload_scene(BvrContext* ctx,
     }
     BVR_CK(cudaEventRecord(ctx->upload_done, ctx->stream));
     ctx->upload_pending = true;
+    if (ctx->pinned_src_in_flight) {
+        // the caller owns its arrays again as soon as the call returns (include/bevyray_b200.h): wait for the copies
+        BVR_CK(cudaEventSynchronize(ctx->upload_done));
+        ctx->upload_pending = false;
+        ctx->pinned_src_in_flight = false;
+    }
 
     // derive the traversal layout in HBM
     if (models_dirty || !partial)
@@ -522,6 +553,7 @@ int bvr_upload_scene(BvrContext* ctx,
         // root ref on the host (needed as a kernel parameter): a leaf root is encoded like any leaf ref
         if (n_nodes) {
             const BvrBvhNode& r = nodes[0];
+            ctx->scene_extent = root_extent(r);
             ctx->root_ref_host = r.model_count > 0
                                      ? (BVR_LEAF_BIT | ((r.model_count - 1u) << 24) | (r.index & BVR_LEAF_FIRST_MASK))
                                      : 0u;   // node 0 is the first inner node -> dense id 0
@@ -547,13 +579,15 @@ int bvr_upload_scene(BvrContext* ctx,
     return BVR_OK;
 }
 
-int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
-                             const BvrModel* models, size_t n_models,
-                             const BvrMaterial* materials, size_t n_materials,
-                             const BvrDirtyRange* ranges, size_t n_ranges,
-                             BvrBvhNode* out_nodes) {
+static int upload_gpu_bvh_impl(BvrContext* ctx,
+                               const BvrModel* models, size_t n_models,
+                               const BvrMaterial* materials, size_t n_materials,
+                               const BvrDirtyRange* ranges, size_t n_ranges,
+                               BvrBvhNode* out_nodes, bool refit) {
     if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
     ctx->error.clear();
+    if (refit && !(ctx->scene_uploaded && ctx->tree_is_ours && n_models == ctx->n_models && n_materials == ctx->n_materials))
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "refit needs a tree built by bvr_upload_scene_gpu_bvh for the same counts");
     if ((n_models && !models) || (n_materials && !materials))
         return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null array with non-zero count");
     if (n_ranges && !ranges) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null ranges with non-zero count");
@@ -610,9 +644,14 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
     uint32_t* d_depth = nullptr;
     *ctx->depth_host = 0;
     if (n_models) {
-        const int nb = launch_bvh_build(ctx->raw_models.as<RawModel>(), (uint32_t)n_models, ctx->raw_nodes.as<RawNode>(),
-                                        ctx->model_rank.as<uint32_t>(), ctx->bvh_scratch.ptr, &d_depth, ctx->stream);
+        if (!refit) ctx->gpu_bvh_algorithm = ctx->tune.gpu_lbvh ? BVH_BUILD_LBVH : BVH_BUILD_PLOC;
+        const int nb = refit ? launch_bvh_refit(ctx->raw_models.as<RawModel>(), (uint32_t)n_models, ctx->raw_nodes.as<RawNode>(),
+                                                ctx->bvh_scratch.ptr, ctx->gpu_bvh_algorithm, ctx->stream)
+                             : launch_bvh_build(ctx->raw_models.as<RawModel>(), (uint32_t)n_models, ctx->raw_nodes.as<RawNode>(),
+                                                ctx->model_rank.as<uint32_t>(), ctx->bvh_scratch.ptr, &d_depth,
+                                                ctx->gpu_bvh_algorithm, ctx->sm_count, ctx->stream);
         if (nb < 0) return fail_cuda(ctx, cudaGetLastError(), "GPU BVH build");
+        if (refit) d_depth = bvh_build_depth_word(ctx->bvh_scratch.ptr, (uint32_t)n_models);
         launches += nb;
         launches += launch_derive_spheres(ctx->raw_models.as<RawModel>(), (uint32_t)n_models, ctx->spheres.as<float4>(),
                                           ctx->sphere_material.as<uint32_t>(), ctx->stream);
@@ -624,6 +663,7 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
             if (st != BVR_OK) return st;
         }
         BVR_CK(cudaMemcpyAsync(ctx->depth_host, d_depth, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        BVR_CK(cudaMemcpyAsync(ctx->root_host, ctx->raw_nodes.ptr, sizeof(BvrBvhNode), cudaMemcpyDeviceToHost, ctx->stream));
         if (out_nodes) {
             BVR_CK(cudaMemcpyAsync(out_nodes, ctx->raw_nodes.ptr, n_nodes * sizeof(BvrBvhNode), cudaMemcpyDeviceToHost, ctx->stream));
             ctx->stats.d2h_bytes += n_nodes * sizeof(BvrBvhNode);
@@ -638,6 +678,7 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
     ctx->n_materials = n_materials;
     ctx->n_nodes = n_nodes;
     ctx->tree_depth = *ctx->depth_host;
+    ctx->scene_extent = n_models ? root_extent(*ctx->root_host) : 0.0f;
     ctx->n_inner = n_models ? (uint32_t)(n_models - 1) : 0u;
     ctx->max_leaf_models = n_models ? 1u : 0u;   // the GPU builder emits one sphere per leaf
     ctx->tree_is_ours = true;
@@ -645,6 +686,16 @@ int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
     ctx->has_scene = n_models > 0;
     ctx->scene_uploaded = true;
     return BVR_OK;
+}
+
+int bvr_upload_scene_gpu_bvh(BvrContext* ctx, const BvrModel* models, size_t n_models, const BvrMaterial* materials,
+                             size_t n_materials, const BvrDirtyRange* ranges, size_t n_ranges, BvrBvhNode* out_nodes) {
+    return upload_gpu_bvh_impl(ctx, models, n_models, materials, n_materials, ranges, n_ranges, out_nodes, false);
+}
+
+int bvr_refit_scene_gpu_bvh(BvrContext* ctx, const BvrModel* models, size_t n_models, const BvrMaterial* materials,
+                            size_t n_materials, const BvrDirtyRange* ranges, size_t n_ranges, BvrBvhNode* out_nodes) {
+    return upload_gpu_bvh_impl(ctx, models, n_models, materials, n_materials, ranges, n_ranges, out_nodes, true);
 }
 
 uint32_t bvr_shard_rows(uint32_t height, const BvrRenderOptions* opts) { return shard_rows_impl(height, opts); }
@@ -681,9 +732,14 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     p.scene.sphere_material = ctx->sphere_material.as<uint32_t>();
     p.scene.materials = ctx->raw_materials.as<float4>();
     p.scene.model_rank = ctx->n_models ? ctx->model_rank.as<uint32_t>() : nullptr;
+    float far_out = ctx->scene_extent;
+    for (int k = 0; k < 3; k++) {
+        const float a = std::fabs(camera->position[k]);
+        if (!(a <= far_out)) far_out = a;
+    }
     if (ctx->nodes4_ch_built && !ctx->tune.no_bvh4) {
         p.scene.nodes4_ch = ctx->nodes4_ch.as<float4>();
-        if (ctx->tight_built && !ctx->tune.no_tight) {
+        if (ctx->tight_built && !ctx->tune.no_tight && far_out <= BVR_TIGHT_MAX_EXTENT) {
             p.scene.nodes4_tight = ctx->nodes4_tight.as<float4>();
             p.scene.tight_groups = ctx->tight_groups.as<float4>();
         }
@@ -744,6 +800,7 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     const bool may_truncate = ctx->tree_depth >= BVR_REF_STACK;
     p.reference_order = (opts->traversal == BVR_TRAVERSAL_REFERENCE_ORDER || (may_truncate && !ctx->tree_is_ours) ||
                          ctx->tree_depth + 1 > BVR_FAST_STACK) ? 1u : 0u;
+    p.strict_slab = far_out <= BVR_FAST_MAX_EXTENT ? 0u : 1u;   // too far from the origin for the fast box arithmetic
     *out = p;
     return BVR_OK;
 }
@@ -784,7 +841,7 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
         launches += launch_copy_raster(p, ctx->stream);
     } else {
         int n = -1;
-        if ((opts->kernel == BVR_KERNEL_WAVEFRONT || opts->kernel == BVR_KERNEL_CTA_WAVEFRONT) && !p.reference_order) {
+        if ((opts->kernel == BVR_KERNEL_WAVEFRONT || opts->kernel == BVR_KERNEL_CTA_WAVEFRONT) && !p.reference_order && !p.strict_slab) {
             const bool cta = opts->kernel == BVR_KERNEL_CTA_WAVEFRONT;
             const size_t slots = cta ? cta_wavefront_slots(ctx->sm_count) : (size_t)p.cam.width * p.shard.rows;
             BVR_CK(ctx->wf_state.ensure(wavefront_state_bytes(slots)));
@@ -806,7 +863,7 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
                 if (e != cudaSuccess) return fail_cuda(ctx, e, "wavefront pipeline");
             }
         }
-        if (n < 0 && !p.reference_order && !ctx->tune.mk_v1) {
+        if (n < 0 && !p.reference_order && !p.strict_slab && !ctx->tune.mk_v1) {
             BVR_CK(cudaMemsetAsync(ctx->pixel_counter.ptr, 0, sizeof(unsigned int), ctx->stream));
             // largest CTA whose stacks (and, when it fits, the scene) fit in shared memory
             const int forced = ctx->tune.mk_threads;
@@ -847,9 +904,9 @@ int bvr_render_device(BvrContext* ctx, const BvrCamera* camera, const BvrRaytrac
     return render_device_impl(ctx, camera, level, window, opts, d_raster_rgba, d_raster_depth, device_out);
 }
 
-int bvr_render(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level, const BvrWindow* window,
-               const BvrRenderOptions* opts, const float* raster_rgba, const float* raster_depth,
-               const BvrOutputs* host_out) {
+static int render_host_impl(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level, const BvrWindow* window,
+                            const BvrRenderOptions* opts, const float* raster_rgba, const float* raster_depth,
+                            const BvrOutputs* host_out, bool async) {
     if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
     ctx->error.clear();
     if (!camera || !level || !window || !opts || !host_out)
@@ -882,8 +939,14 @@ int bvr_render(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel*
         if (!pl.pinned) { pl.off = out_staging; out_staging += (pl.bytes + 255) & ~(size_t)255; }
         BVR_CK(pl.dev->ensure(pl.bytes));
     }
-    BVR_CK(cudaStreamSynchronize(ctx->stream));   // staging reuse
-    BVR_CK(ctx->io_staging.ensure(in_staging > out_staging ? in_staging : out_staging));
+    if (async) {
+        // nothing may be staged: the call must not wait for the device, and the copies must outlive it
+        if (in_staging || out_staging)
+            return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "bvr_render_async needs page-locked (pinned) host buffers");
+    } else {
+        BVR_CK(cudaStreamSynchronize(ctx->stream));   // staging reuse
+        BVR_CK(ctx->io_staging.ensure(in_staging > out_staging ? in_staging : out_staging));
+    }
 
     size_t off = 0;
     int st;
@@ -915,11 +978,25 @@ int bvr_render(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel*
         ctx->stats.d2h_bytes += pl.bytes;
         staged |= !pl.pinned;
     }
+    ctx->pinned_src_in_flight = false;            // (an upload-only notion: see bvr_upload_scene)
+    if (async) return BVR_OK;                     // bvr_sync completes the frame
     BVR_CK(cudaStreamSynchronize(ctx->stream));
     if (staged)
         for (Plane& pl : planes)
             if (pl.host && !pl.pinned) std::memcpy(pl.host, static_cast<char*>(ctx->io_staging.ptr) + pl.off, pl.bytes);
     return BVR_OK;
+}
+
+int bvr_render(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level, const BvrWindow* window,
+               const BvrRenderOptions* opts, const float* raster_rgba, const float* raster_depth,
+               const BvrOutputs* host_out) {
+    return render_host_impl(ctx, camera, level, window, opts, raster_rgba, raster_depth, host_out, false);
+}
+
+int bvr_render_async(BvrContext* ctx, const BvrCamera* camera, const BvrRaytraceLevel* level, const BvrWindow* window,
+                     const BvrRenderOptions* opts, const float* raster_rgba, const float* raster_depth,
+                     const BvrOutputs* host_out) {
+    return render_host_impl(ctx, camera, level, window, opts, raster_rgba, raster_depth, host_out, true);
 }
 
 int bvr_axpby_device(BvrContext* ctx, float* d_dst, float dst_weight, const float* d_src, float src_weight, size_t n) {

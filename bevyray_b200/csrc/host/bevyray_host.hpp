@@ -387,6 +387,6 @@ SceneBuffers scene_rtiow(uint64_t seed);
 // as src/main.rs:116-179 (configs C4, C5)
 SceneBuffers scene_random(uint64_t seed, uint32_t n, float side, float rmin, float rmax);
 // C5: centres of scene_random moved by a closed-form function of the frame index; rebuilds the BVH.
-void animate_random(SceneBuffers& scene, const std::vector<BvrModel>& base, uint32_t frame);
+void animate_random(SceneBuffers& scene, const std::vector<BvrModel>& base, uint32_t frame, bool rebuild_bvh = true);
 
 }  // namespace bevyray

@@ -70,6 +70,12 @@ int bvrh_scene_animate(BvrhScene* scene, uint32_t frame) {
     return 0;
 }
 
+int bvrh_scene_animate_models(BvrhScene* scene, uint32_t frame) {
+    if (!scene) return 1;
+    try { animate_random(scene->buffers, scene->base, frame, false); } catch (...) { return 1; }
+    return 0;
+}
+
 void bvrh_scene_free(BvrhScene* scene) { delete scene; }
 size_t bvrh_scene_n_models(const BvrhScene* s) { return s ? s->buffers.models.size() : 0; }
 size_t bvrh_scene_n_materials(const BvrhScene* s) { return s ? s->buffers.materials.size() : 0; }

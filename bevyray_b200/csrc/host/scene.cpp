@@ -165,7 +165,7 @@ SceneBuffers scene_random(uint64_t seed, uint32_t n, float side, float rmin, flo
     return out;
 }
 
-void animate_random(SceneBuffers& scene, const std::vector<BvrModel>& base, uint32_t frame) {
+void animate_random(SceneBuffers& scene, const std::vector<BvrModel>& base, uint32_t frame, bool rebuild_bvh) {
     const float t = (float)frame * (1.0f / 60.0f);
     scene.models = base;
     for (size_t i = 0; i < base.size(); i++) {
@@ -175,7 +175,7 @@ void animate_random(SceneBuffers& scene, const std::vector<BvrModel>& base, uint
         scene.models[i].position[0] = base[i].position[0] + 0.5f * std::sin(2.0f * t + phase);
         scene.models[i].position[1] = base[i].position[1] + 0.5f * std::cos(3.0f * t + phase);
     }
-    scene.nodes = build_ploc(scene.models, 24);
+    if (rebuild_bvh) scene.nodes = build_ploc(scene.models, 24);   // (callers that build the tree on the GPU skip this)
 }
 
 }  // namespace bevyray

@@ -28,6 +28,8 @@ struct RenderParams {
     uchar4* out_srgb8;
     unsigned long long* ray_counter;   // += raycast() invocations
     uint32_t reference_order;          // BvrTraversal
+    uint32_t strict_slab;              // scene / camera too far from the origin for the culling-only slab arithmetic:
+                                       // the one-thread-per-pixel kernel runs, with the reference's (box - o) * (1/d)
     float4* selfcheck_log;             // BVR_SELFCHECK: 2 x float4 per logged ray (o.xyz, t) (d.xyz, model bits), or null
     unsigned int* selfcheck_count;     // rays logged so far (may exceed the capacity: the excess is dropped)
     uint32_t selfcheck_cap;
@@ -104,8 +106,13 @@ int launch_validate_scene(const RawNode* nodes, uint32_t n_nodes, uint32_t n_mod
 
 // ---- GPU BVH builder (bvh_build.cu) ----
 size_t bvh_build_scratch_bytes(uint32_t n_models);
+#define BVH_BUILD_LBVH 0   // Karras radix tree over the Morton order (fastest build)
+#define BVH_BUILD_PLOC 1   // parallel locally-ordered clustering over the Morton order (the reference's algorithm; better trees)
 int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, uint32_t* model_rank, void* scratch,
-                     uint32_t** depth_out, cudaStream_t stream);
+                     uint32_t** depth_out, int algorithm, int sm_count, cudaStream_t stream);
+// same topology as the last launch_bvh_build on this scratch, boxes refitted to the current models
+uint32_t* bvh_build_depth_word(void* scratch, uint32_t n_models);   // device word holding the tree depth of the last build / refit
+int launch_bvh_refit(const RawModel* models, uint32_t n, RawNode* out_nodes, void* scratch, int algorithm, cudaStream_t stream);
 
 // ---- render kernels ----
 int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple one-thread-per-pixel kernel (v1)

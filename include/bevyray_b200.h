@@ -228,22 +228,34 @@ int bvr_reload_tuning(BvrContext* ctx);
 /* Upload the scene in the reference's layout.  `ranges == NULL` uploads everything; otherwise only
  * the listed element ranges are copied (pinned staging -> HBM) and the device-side traversal layout
  * is re-derived.  Counts must match the previous upload when ranges are given.
- * n_models == 0 is legal: every ray misses. */
+ * n_models == 0 is legal: every ray misses.
+ * The caller owns its arrays again when the call returns: pageable arrays are staged, pinned arrays are copied from
+ * directly and the call waits for those copies (the device-side re-layout still runs asynchronously). */
 int bvr_upload_scene(BvrContext* ctx,
                      const BvrModel* models, size_t n_models,
                      const BvrMaterial* materials, size_t n_materials,
                      const BvrBvhNode* nodes, size_t n_nodes,
                      const BvrDirtyRange* ranges, size_t n_ranges);
 
-/* Same as bvr_upload_scene, but the BVH is BUILT ON THE GPU from the models (LBVH emitting the BVHNode
- * contract) instead of being supplied: replaces obvhs::ploc::build_ploc + the node mapping at
- * src/raytracing/extract.rs:316-332 for callers that opt in.  `ranges` may name models / materials only.
+/* Same as bvr_upload_scene, but the BVH is BUILT ON THE GPU from the models (PLOC over the Morton order, the
+ * reference's own algorithm, emitting the BVHNode contract) instead of being supplied: replaces
+ * obvhs::ploc::build_ploc + the node mapping at src/raytracing/extract.rs:316-332 for callers that opt in.  `ranges` may name models / materials only.
  * `out_nodes` (nullable) receives the 2*n_models-1 nodes in the reference layout. */
 int bvr_upload_scene_gpu_bvh(BvrContext* ctx,
                              const BvrModel* models, size_t n_models,
                              const BvrMaterial* materials, size_t n_materials,
                              const BvrDirtyRange* ranges, size_t n_ranges,
                              BvrBvhNode* out_nodes);
+
+/* Same arguments; keeps the TOPOLOGY of the tree the last bvr_upload_scene_gpu_bvh built for these counts and only refits
+ * its boxes to the moved / resized spheres (bottom-up, one kernel) — the cheap path for small motion; the caller decides
+ * when the tree has degraded enough to rebuild.  The image does not depend on the choice (any valid tree gives the
+ * reference's closest hits). */
+int bvr_refit_scene_gpu_bvh(BvrContext* ctx,
+                            const BvrModel* models, size_t n_models,
+                            const BvrMaterial* materials, size_t n_materials,
+                            const BvrDirtyRange* ranges, size_t n_ranges,
+                            BvrBvhNode* out_nodes);
 
 /* Rows this shard renders for an image of `height` rows (== height when unsharded). */
 uint32_t bvr_shard_rows(uint32_t height, const BvrRenderOptions* opts);
@@ -268,6 +280,16 @@ int bvr_render(BvrContext* ctx,
                const BvrRenderOptions* opts,
                const float* raster_rgba, const float* raster_depth,
                const BvrOutputs* host_out);
+
+/* bvr_render without the wait: every host buffer (raster inputs, output planes) must be page-locked; the call enqueues
+ * the input copies, the kernels and the output copies on the context stream and returns.  The frame is complete, and the
+ * buffers are the caller's again, after bvr_sync.  Two contexts on one device (each has its own stream) pipeline an
+ * animated scene: frame f renders in one while frame f+1's scene is uploaded / its BVH built in the other. */
+int bvr_render_async(BvrContext* ctx,
+                     const BvrCamera* camera, const BvrRaytraceLevel* level, const BvrWindow* window,
+                     const BvrRenderOptions* opts,
+                     const float* raster_rgba, const float* raster_depth,
+                     const BvrOutputs* host_out);
 
 /* Same, but every pointer (raster inputs and outputs) is a DEVICE pointer owned by the caller and
  * the call only enqueues work on the context stream (use bvr_sync or stream semantics). */

@@ -26,6 +26,9 @@ BvrhScene* bvrh_scene_from_models(const BvrModel* models, size_t n_models,
 /* C5 animation: positions = closed-form function of `frame` applied to the scene's base positions;
  * rebuilds the BVH.  Returns 0 on success. */
 int  bvrh_scene_animate(BvrhScene* scene, uint32_t frame);
+/* the same motion without the host-side BVH rebuild (the node array goes stale): for callers that build the tree on the
+ * GPU (bvr_upload_scene_gpu_bvh) */
+int  bvrh_scene_animate_models(BvrhScene* scene, uint32_t frame);
 void bvrh_scene_free(BvrhScene* scene);
 size_t bvrh_scene_n_models(const BvrhScene* scene);
 size_t bvrh_scene_n_materials(const BvrhScene* scene);

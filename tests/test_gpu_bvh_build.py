@@ -1,11 +1,36 @@
-"""GPU BVH builder: bvr_upload_scene_gpu_bvh builds the BVHNode array on the device.
+"""GPU BVH builder: bvr_upload_scene_gpu_bvh builds the BVHNode array on the device — PLOC over the
+Morton order (default; the reference's own algorithm, extract.rs:316-321) or the plain LBVH (BVR_GPU_LBVH=1).
 Checked against the reference contract with the HOST validator, rendered through the oracle with the
 downloaded nodes (bit-exact), and compared with the image obtained from the host PLOC tree (the closest hit
 does not depend on topology)."""
 import numpy as np
 import pytest
 
+import os
+
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["ploc", "lbvh"])
+def builder(request, ctx):
+    """Both GPU builders behind bvr_upload_scene_gpu_bvh (the knob is read at bvr_create / bvr_reload_tuning)."""
+    saved = os.environ.pop("BVR_GPU_LBVH", None)
+    if request.param == "lbvh":
+        os.environ["BVR_GPU_LBVH"] = "1"
+    ctx.reload_tuning()
+    yield request.param
+    os.environ.pop("BVR_GPU_LBVH", None)
+    if saved is not None:
+        os.environ["BVR_GPU_LBVH"] = saved
+    ctx.reload_tuning()
+
+
+def sah_cost(nodes):
+    """Surface-area-heuristic cost of a tree in the reference layout: sum of inner-node areas / root area."""
+    d = nodes["bounds_max"].astype(np.float64) - nodes["bounds_min"].astype(np.float64)
+    area = d[:, 0] * d[:, 1] + d[:, 1] * d[:, 2] + d[:, 2] * d[:, 0]
+    inner = nodes["model_count"] == 0
+    return float(area[inner].sum() / area[0])
 
 
 def bits(a):
@@ -29,7 +54,7 @@ def random_models(bvr, n, seed, spread=10.0, coincident=False):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 64, 1000, 20000])
-def test_contract_and_parity(bvr, oracle, ctx, n):
+def test_contract_and_parity(bvr, oracle, ctx, builder, n):
     models, mats = random_models(bvr, n, seed=n)
     nodes = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
     assert len(nodes) == 2 * n - 1
@@ -51,7 +76,7 @@ def test_contract_and_parity(bvr, oracle, ctx, n):
         assert np.array_equal(bits(got[k]), bits(ref[k])), k
 
 
-def test_coincident_spheres_and_demo_scene(bvr, oracle, ctx, rtiow):
+def test_coincident_spheres_and_demo_scene(bvr, oracle, ctx, builder, rtiow):
     models, mats = random_models(bvr, 40, seed=1, coincident=True)   # identical Morton keys
     nodes = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
     assert bvr.validate_bvh(nodes, models) is None
@@ -66,7 +91,7 @@ def test_coincident_spheres_and_demo_scene(bvr, oracle, ctx, rtiow):
         assert np.array_equal(bits(got[k]), bits(want[k])), k
 
 
-def test_dirty_models_rebuild(bvr, ctx):
+def test_dirty_models_rebuild(bvr, ctx, builder):
     models, mats = random_models(bvr, 500, seed=3)
     ctx.upload_scene_gpu_bvh(models, mats)
     h0 = ctx.stats()["h2d_bytes"]
@@ -76,6 +101,61 @@ def test_dirty_models_rebuild(bvr, ctx):
     assert bvr.validate_bvh(nodes, models) is None
     with pytest.raises(bvr.BvrError):
         ctx.upload_scene_gpu_bvh(models, mats, ranges=[(bvr.capi.ARRAY_BVH_NODES, 0, 1)])
+
+
+def test_ploc_tree_is_deterministic_and_better_than_lbvh(bvr, ctx):
+    """Two PLOC builds of the same models give the same bytes (node ids come from a scan, not from atomics), and the
+    tree is at least as good as the LBVH one by the surface-area heuristic (what PLOC is for)."""
+    for n, seed in ((506, 1), (5000, 2), (60000, 3)):
+        models, mats = random_models(bvr, n, seed=seed, spread=30.0)
+        os.environ.pop("BVR_GPU_LBVH", None)
+        ctx.reload_tuning()
+        a = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
+        b = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
+        assert a.tobytes() == b.tobytes()
+        os.environ["BVR_GPU_LBVH"] = "1"
+        ctx.reload_tuning()
+        try:
+            lb = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
+        finally:
+            os.environ.pop("BVR_GPU_LBVH", None)
+            ctx.reload_tuning()
+        host = bvr.build_ploc(models)
+        c_ploc, c_lbvh, c_host = sah_cost(a), sah_cost(lb), sah_cost(host)
+        assert c_ploc < c_lbvh, (n, c_ploc, c_lbvh)
+        assert c_ploc < 1.15 * c_host, (n, c_ploc, c_host)      # in the league of the host PLOC (obvhs restatement)
+
+
+def test_refit_keeps_topology_and_matches_the_oracle(bvr, oracle, ctx, builder):
+    """bvr_refit_scene_gpu_bvh: spheres move a little, the tree keeps its topology (same index / model_count columns),
+    its boxes follow the spheres, and the image equals the oracle's on the refitted nodes."""
+    models, mats = random_models(bvr, 3000, seed=9, spread=14.0)
+    nodes0 = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
+    rs = np.random.RandomState(4)
+    moved = np.sort(rs.choice(len(models), 400, replace=False))
+    models["position"][moved] += rs.uniform(-0.3, 0.3, (400, 3)).astype(np.float32)
+    models["radius"][moved[:50]] *= np.float32(1.3)
+    h0 = ctx.stats()["h2d_bytes"]
+    ranges = [(bvr.capi.ARRAY_MODELS, int(i), 1) for i in moved]
+    nodes1 = ctx.upload_scene_gpu_bvh(models, mats, ranges=ranges, want_nodes=True, refit=True)
+    assert ctx.stats()["h2d_bytes"] - h0 == 400 * 32
+    assert np.array_equal(nodes1["index"], nodes0["index"]) and np.array_equal(nodes1["model_count"], nodes0["model_count"])
+    assert not np.array_equal(nodes1["bounds_min"], nodes0["bounds_min"])
+    assert bvr.validate_bvh(nodes1, models) is None
+    W, H = 128, 80
+    cam = bvr.make_camera(position=(0, 0, 0), target=(0, 0, -1), aspect=W / H, sample_count=2, bounces=5)
+    win = bvr.make_window(0.55, H)
+    got = ctx.render(cam, 3, win, bvr.make_options(W))
+    want, cnt = oracle.render(models, mats, nodes1, cam, bvr.make_level(3), win, W)
+    for k in ("primary_id", "primary_depth", "rt_depth", "rgba"):
+        assert np.array_equal(bits(got[k]), bits(want[k])), k
+    assert ctx.stats()["rays"] == cnt["rays"]
+    # a refit needs a tree of the library's own for the same counts
+    with pytest.raises(bvr.BvrError):
+        ctx.upload_scene_gpu_bvh(models[:100], mats[:100], refit=True)
+    ctx.upload_scene(models, mats, bvr.build_ploc(models))
+    with pytest.raises(bvr.BvrError):
+        ctx.upload_scene_gpu_bvh(models, mats, refit=True)
 
 
 def test_app_mirror_with_gpu_bvh(bvr, oracle):

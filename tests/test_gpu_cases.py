@@ -405,3 +405,48 @@ def test_app_mirror_renders_demo_scene(bvr, oracle):
         lib.bvrh_app_destroy(app2)
     finally:
         lib.bvrh_app_destroy(app)
+
+
+def test_render_async_with_two_contexts(bvr, rtiow):
+    """bvr_render_async enqueues input copies, kernels and output copies and returns; bvr_sync completes the frame.
+    Two contexts on one device pipeline an animated scene (frame f renders while frame f+1 is uploaded): every frame must
+    equal the synchronous render of the same scene, and pageable buffers are refused."""
+    import torch
+    W, H = 192, 108
+    cam = bvr.make_camera(sample_count=2, bounces=4, aspect=W / H)
+    rs = np.random.RandomState(3)
+    raster = torch.from_numpy(rs.rand(H, W, 4).astype(np.float32)).pin_memory().numpy()
+    depth = torch.from_numpy((rs.rand(H, W) * 0.02).astype(np.float32)).pin_memory().numpy()
+    scene = bvr.Scene.random(4, 3000, 30.0, 0.1, 0.4)
+    cam = bvr.make_camera(position=(0, 0, 28), target=(0, 0, 0), aspect=W / H, sample_count=2, bounces=4)
+    ctxs = [bvr.Context(0), bvr.Context(0)]
+    outs = [{"rgba": torch.empty((H, W, 4), dtype=torch.float32).pin_memory().numpy(),
+             "primary_id": torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32)} for _ in ctxs]
+    ref_ctx = bvr.Context(0)
+    opts = bvr.make_options(W)
+    frames = []
+    pending = [None, None]
+    for f in range(6):
+        k = f % 2
+        ctxs[k].sync()
+        if pending[k] is not None:
+            frames.append((pending[k], outs[k]["rgba"].copy(), outs[k]["primary_id"].copy()))
+        scene.animate(f + 1, rebuild_bvh=False)
+        ctxs[k].upload_scene_gpu_bvh(scene.models, scene.materials)
+        ctxs[k].render(cam, 2, bvr.make_window(0.1 * (f + 1), H), opts, raster, depth, want=("rgba", "primary_id"), out=outs[k],
+                       asynchronous=True)
+        pending[k] = (f, scene.models.copy())
+    for k in range(2):
+        ctxs[k].sync()
+        frames.append((pending[k], outs[k]["rgba"].copy(), outs[k]["primary_id"].copy()))
+    assert len(frames) == 6
+    for (f, models), rgba, pid in frames:
+        ref_ctx.upload_scene_gpu_bvh(models, scene.materials)
+        want = ref_ctx.render(cam, 2, bvr.make_window(0.1 * (f + 1), H), opts, raster, depth, want=("rgba", "primary_id"))
+        assert np.array_equal(bits(rgba), bits(want["rgba"])) and np.array_equal(pid, want["primary_id"]), f
+    with pytest.raises(bvr.BvrError) as e:
+        ctxs[0].render(cam, 2, bvr.make_window(0.5, H), opts, raster, depth, want=("rgba",), out={"rgba": np.empty((H, W, 4), np.float32)},
+                       asynchronous=True)
+    assert e.value.status == bvr.capi.BVR_ERR_INVALID_ARGUMENT
+    for c in ctxs + [ref_ctx]:
+        c.close()

@@ -100,3 +100,40 @@ def test_random_big_scenes(bvr, oracle, ctx, it):
     for k in ("primary_id", "primary_depth", "rt_depth", "rgba"):
         assert np.array_equal(np.ascontiguousarray(got[k]).view(np.uint32), np.ascontiguousarray(want[k]).view(np.uint32)), k
     assert rays == cnt["rays"]
+
+
+@pytest.mark.parametrize("shift", [3.0e3, 2.0e4, 1.0e5, 1.0e6])
+def test_scenes_far_from_the_origin(bvr, oracle, ctx, shift):
+    """The culling-only slab test computes c/d - o/d, whose rounding error grows with the distance from the origin: the
+    library drops the tight boxes beyond 4096 units and the fast box arithmetic beyond 32768 (bvr_api.cu).  The same
+    scene translated far away must still match the oracle bit for bit."""
+    rs = np.random.RandomState(5)
+    n = 300
+    models = np.zeros(n, bvr.MODEL_DTYPE)
+    models["position"] = (rs.uniform(-6, 6, (n, 3)) + np.array([shift, -shift * 0.5, shift * 0.25])).astype(np.float32)
+    models["radius"] = rs.uniform(0.2, 0.6, n).astype(np.float32)
+    models["material_id"] = np.arange(n)
+    mats = np.zeros(n, bvr.MATERIAL_DTYPE)
+    mats["base_color"] = rs.uniform(0.1, 0.9, (n, 3)).astype(np.float32)
+    mats["metallic"] = (rs.rand(n) < 0.2).astype(np.float32)
+    mats["roughness"] = 0.5
+    mats["ior"] = 1.5
+    mats["specular_transmission"] = (rs.rand(n) < 0.1).astype(np.float32)
+    scene = bvr.Scene.from_arrays(models, mats)
+    W, H = 160, 90
+    centre = (shift, -shift * 0.5, shift * 0.25)
+    cam = bvr.make_camera(position=(centre[0], centre[1], centre[2] + 22.0), target=centre, aspect=W / H, sample_count=3, bounces=6)
+    win = bvr.make_window(0.23, H)
+    want, cnt = oracle.render(scene.models, scene.materials, scene.nodes, cam, bvr.make_level(3), win, W)
+    assert cnt["hits_shaded"] > 1000
+    for gpu_bvh in (False, True):
+        if gpu_bvh:
+            nodes = ctx.upload_scene_gpu_bvh(scene.models, scene.materials, want_nodes=True)
+            want2, cnt2 = oracle.render(scene.models, scene.materials, nodes, cam, bvr.make_level(3), win, W)
+        else:
+            ctx.upload_scene(scene.models, scene.materials, scene.nodes)
+            want2, cnt2 = want, cnt
+        got = ctx.render(cam, 3, win, bvr.make_options(W))
+        for k in ("primary_id", "primary_depth", "rt_depth", "rgba"):
+            assert np.array_equal(np.ascontiguousarray(got[k]).view(np.uint32), np.ascontiguousarray(want2[k]).view(np.uint32)), (shift, gpu_bvh, k)
+        assert ctx.stats()["rays"] == cnt2["rays"]
