@@ -551,6 +551,9 @@ def run_c5(args, frames, mode):
     gpu_bvh = mode != "host"
     scene = bvr.Scene.random(11, 10000, 43.0, 0.05, 0.25)
     cam = bvr.make_camera(position=(0.0, 0.0, 40.0), target=(0.0, 0.0, 0.0), aspect=W / H, sample_count=4, bounces=4)
+    refit_every = 16 if mode == "pipelined_refit" else 0     # rebuild every 16th upload of a context, refit in between
+    if mode == "pipelined_refit":
+        mode = "pipelined"
     n_ctx = 2 if mode == "pipelined" else 1
     ctxs = [bvr.Context(0) for _ in range(n_ctx)]
     rs = np.random.RandomState(0)
@@ -580,15 +583,21 @@ def run_c5(args, frames, mode):
         m = scene.models
         if mode == "pipelined":
             ctx.sync()                                        # frame f-2 of this context is complete: its buffers are free
-            rays += ctx.stats()["rays"] if f >= n_ctx else 0
+            if f >= n_ctx:
+                st = ctx.stats()
+                rays += st["rays"]
+                gpu_build_ms += st["last_upload_ms"]
         ranges = dirty_model_ranges(capi, m, prevs[k])
         win = bvr.make_window((0.37 + 0.013 * f) % 1.0, H)
-        st0 = ctx.stats()["h2d_bytes"]
+        st0 = ctx.stats()["h2d_bytes"] if mode != "pipelined" else 0     # (bvr_get_stats waits for the stream)
         if gpu_bvh:
-            ctx.upload_scene_gpu_bvh(m, scene.materials, ranges)
-            st1 = ctx.stats()
-            gpu_build_ms += st1["last_upload_ms"]
-            h2d += st1["h2d_bytes"] - st0
+            ctx.upload_scene_gpu_bvh(m, scene.materials, ranges, refit=bool(refit_every) and (f // n_ctx) % refit_every != 0)
+            if mode == "pipelined":
+                h2d += sum(c for _, _, c in ranges) * 32                  # enqueued only: nothing here waits for the GPU
+            else:
+                st1 = ctx.stats()
+                gpu_build_ms += st1["last_upload_ms"]
+                h2d += st1["h2d_bytes"] - st0
         else:
             n = scene.nodes
             dn = np.flatnonzero((n.view(np.uint8).reshape(-1, 48) != prev_nodes.view(np.uint8).reshape(-1, 48)).any(axis=1))
@@ -620,7 +629,9 @@ def run_c5(args, frames, mode):
                                    "upload, fused depth composite vs synthetic raster, host buffers in and out"},
             "mode": {"host": "host PLOC (csrc/host/ploc.cpp) + bvr_upload_scene + bvr_render",
                      "gpu": "bvr_upload_scene_gpu_bvh (tree built on the GPU) + bvr_render",
-                     "pipelined": "two contexts: bvr_upload_scene_gpu_bvh of frame f+1 overlaps bvr_render_async of frame f"}[mode],
+                     "pipelined": "two contexts: bvr_upload_scene_gpu_bvh of frame f+1 overlaps bvr_render_async of frame f"
+                                  + ("; the tree is rebuilt every 16th upload of a context and refitted in between "
+                                     "(bvr_refit_scene_gpu_bvh)" if refit_every else "")}[mode],
             "split_ms": {"host_animate" + ("_and_bvh_build" if not gpu_bvh else ""): t_build / frames * 1e3,
                          "dirty_detect_and_upload": t_upload / frames * 1e3,
                          ("render_enqueue" if mode == "pipelined" else "render_with_host_io"): t_render / frames * 1e3},
@@ -654,7 +665,8 @@ def run_ours(args):
                                                   "gpu_launches", "clocks", "config", "roofline", "roofline_hbm") if k in leg}
             except Exception as e:   # a leg must never take the headline line down with it
                 extra[key] = {"error": repr(e)}
-        for name, mode in (("c5_host_bvh", "host"), ("c5_gpu_bvh", "gpu"), ("c5_gpu_bvh_pipelined", "pipelined")):
+        for name, mode in (("c5_host_bvh", "host"), ("c5_gpu_bvh", "gpu"), ("c5_gpu_bvh_pipelined", "pipelined"),
+                           ("c5_gpu_bvh_pipelined_refit", "pipelined_refit")):
             try:
                 extra[name] = run_c5(args, 60, mode)
             except Exception as e:
@@ -673,7 +685,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--gpu-bvh", action="store_true", help="build the BVH on the GPU instead of the host PLOC")
     ap.add_argument("--frames", type=int, default=300, help="frames of the animated workload (c5)")
-    ap.add_argument("--c5-mode", default=None, choices=["host", "gpu", "pipelined"], help="c5: see run_c5")
+    ap.add_argument("--c5-mode", default=None, choices=["host", "gpu", "pipelined", "pipelined_refit"], help="c5: see run_c5")
     ap.add_argument("--kernel", default="auto", choices=["auto", "megakernel", "wavefront", "cta-wavefront"])
     ap.add_argument("--reference-order", action="store_true", help="reference traversal order (raytrace.wgsl:313-346)")
     ap.add_argument("--shard", default="samples", choices=["samples", "tiles"])

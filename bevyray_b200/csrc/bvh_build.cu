@@ -265,8 +265,15 @@ __device__ __forceinline__ void ploc_decide(const uint32_t* __restrict__ nn, uin
     keep = !mutual || i < j;
 }
 
+// SINGLE: one CTA does everything and the barriers are __syncthreads (small scenes: a grid barrier costs microseconds,
+// a round of a 10 k-sphere scene much less)
+template <bool SINGLE>
 __global__ void __launch_bounds__(PLOC_THREADS) ploc_kernel(const PlocArrays p) {
     cg::grid_group grid = cg::this_grid();
+    auto barrier = [&]() {
+        if constexpr (SINGLE) { __threadfence_block(); __syncthreads(); }
+        else grid.sync();
+    };
     __shared__ uint32_t warp_keep[PLOC_THREADS / 32], warp_merge[PLOC_THREADS / 32];
     __shared__ uint32_t tile_base_keep, tile_base_merge;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(PLOC_THREADS) ploc_kernel(const PlocArrays p) 
         p.clo[0][i] = lo;
         p.chi[0][i] = hi;
     }
-    grid.sync();
+    barrier();
     uint32_t n = p.n, cur = 0, next_id = 0;
     while (n > 1u) {
         const uint32_t* cid = p.cid[cur];
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(PLOC_THREADS) ploc_kernel(const PlocArrays p) 
             }
             p.nn[i] = bj;
         }
-        grid.sync();
+        barrier();
         // --- 2: every CTA owns a contiguous chunk: clusters kept / merged in it ---
         const uint32_t chunk = (n + gridDim.x - 1u) / gridDim.x;
         const uint32_t c0 = min(n, blockIdx.x * chunk), c1 = min(n, c0 + chunk);
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(PLOC_THREADS) ploc_kernel(const PlocArrays p) 
                 p.block_counts[blockIdx.x] = make_uint2(k, m);
             }
         }
-        grid.sync();
+        barrier();
         // --- 3: compact in order; merges create their inner node ---
         uint32_t total_keep = 0, total_merge = 0;
         {
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(PLOC_THREADS) ploc_kernel(const PlocArrays p) 
         next_id += total_merge;
         n = total_keep;
         cur ^= 1u;
-        grid.sync();
+        barrier();
     }
     if (blockIdx.x == 0 && tid == 0u) {
         const uint32_t root = p.n - 2u;
@@ -554,14 +561,18 @@ int launch_bvh_build(const RawModel* models, uint32_t n, RawNode* out_nodes, uin
         pa.parent_leaf = parent_leaf;
         pa.depth_out = depth;
         // all CTAs must be resident at once (grid barriers): at most what the device holds, at most one CTA per 2048 leaves
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ploc_kernel, PLOC_THREADS, 0) != cudaSuccess || per_sm < 1) return -1;
-        int grid = sm_count * (per_sm > 2 ? 2 : per_sm);
-        const int useful = (int)((n + 2047u) / 2048u);
-        if (grid > useful) grid = useful;
-        if (grid > 4096) grid = 4096;
-        void* args[] = {&pa};
-        if (cudaLaunchCooperativeKernel((const void*)ploc_kernel, dim3(grid), dim3(PLOC_THREADS), args, 0, stream) != cudaSuccess) return -1;
+        if (n <= 32768u) {
+            ploc_kernel<true><<<1, PLOC_THREADS, 0, stream>>>(pa);
+        } else {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ploc_kernel<false>, PLOC_THREADS, 0) != cudaSuccess || per_sm < 1) return -1;
+            int grid = sm_count * (per_sm > 2 ? 2 : per_sm);
+            const int useful = (int)((n + 2047u) / 2048u);
+            if (grid > useful) grid = useful;
+            if (grid > 4096) grid = 4096;
+            void* args[] = {&pa};
+            if (cudaLaunchCooperativeKernel((const void*)ploc_kernel<false>, dim3(grid), dim3(PLOC_THREADS), args, 0, stream) != cudaSuccess) return -1;
+        }
         ploc_emit<<<blocks, T, 0, stream>>>(models, vals_sorted, n, children, box_lo, box_hi, out_nodes);
         ploc_rank<<<blocks, T, 0, stream>>>(vals_sorted, n, children, parent_inner, parent_leaf, pa.below, model_rank);
         launches += 3;

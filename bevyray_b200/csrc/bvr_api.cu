@@ -98,6 +98,8 @@ struct BvrContext {
     PinnedBuffer upload_staging;
     cudaEvent_t upload_done = nullptr;
     bool upload_pending = false;
+    cudaEvent_t build_done = nullptr;         // GPU BVH build finished (depth_host / root_host valid)
+    bool build_pending = false;
     bool pinned_src_in_flight = false;        // an upload copies straight out of a pinned caller buffer
 
     // per-frame IO for the host-buffer entry point
@@ -117,6 +119,25 @@ namespace {
 int fail(BvrContext* ctx, int status, const std::string& msg) {
     if (ctx) ctx->error = msg;
     return status;
+}
+
+int fail_cuda(BvrContext* ctx, cudaError_t e, const char* what);
+
+// bvr_upload_scene_gpu_bvh leaves the tree depth and the root box in pinned memory behind an event
+int resolve_gpu_build(BvrContext* ctx) {
+    if (!ctx->build_pending) return BVR_OK;
+    cudaError_t e = cudaEventSynchronize(ctx->build_done);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "GPU BVH build");
+    ctx->build_pending = false;
+    ctx->tree_depth = *ctx->depth_host;
+    float m = 0.0f;
+    for (int k = 0; k < 3; k++) {
+        const float a = std::fabs(ctx->root_host->bounds_min[k]), b = std::fabs(ctx->root_host->bounds_max[k]);
+        if (!(a <= m)) m = a;
+        if (!(b <= m)) m = b;
+    }
+    ctx->scene_extent = m;
+    return BVR_OK;
 }
 
 int fail_cuda(BvrContext* ctx, cudaError_t e, const char* what) {
@@ -347,6 +368,7 @@ int bvr_create(int device, BvrContext** out_ctx) {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_upload0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_upload1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->upload_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->build_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = ctx->ray_counter.ensure(3 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = ctx->root_ref.ensure(sizeof(uint32_t));
     if (e == cudaSuccess) e = ctx->pixel_counter.ensure(sizeof(unsigned int));
@@ -389,7 +411,7 @@ void bvr_destroy(BvrContext* ctx) {
     if (ctx->q16_done) cudaEventDestroy(ctx->q16_done);
     if (ctx->depth_host) cudaFreeHost(ctx->depth_host);
     if (ctx->root_host) cudaFreeHost(ctx->root_host);
-    cudaEvent_t evs[] = {ctx->ev_render0, ctx->ev_render1, ctx->ev_upload0, ctx->ev_upload1, ctx->upload_done};
+    cudaEvent_t evs[] = {ctx->ev_render0, ctx->ev_render1, ctx->ev_upload0, ctx->ev_upload1, ctx->upload_done, ctx->build_done};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     cudaGetLastError();
@@ -430,6 +452,7 @@ int bvr_upload_scene(BvrContext* ctx,
         return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null array with non-zero count");
     if (n_ranges && !ranges) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null ranges with non-zero count");
     cudaSetDevice(ctx->device);
+    { const int rs = resolve_gpu_build(ctx); if (rs != BVR_OK) return rs; }
 
     const bool partial = ranges != nullptr && ctx->scene_uploaded && n_models == ctx->n_models &&
                          n_materials == ctx->n_materials && n_nodes == ctx->n_nodes;
@@ -586,6 +609,8 @@ static int upload_gpu_bvh_impl(BvrContext* ctx,
                                BvrBvhNode* out_nodes, bool refit) {
     if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
     ctx->error.clear();
+    cudaSetDevice(ctx->device);
+    { const int rs = resolve_gpu_build(ctx); if (rs != BVR_OK) return rs; }   // (the pinned read-back words are reused below)
     if (refit && !(ctx->scene_uploaded && ctx->tree_is_ours && n_models == ctx->n_models && n_materials == ctx->n_materials))
         return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "refit needs a tree built by bvr_upload_scene_gpu_bvh for the same counts");
     if ((n_models && !models) || (n_materials && !materials))
@@ -671,14 +696,24 @@ static int upload_gpu_bvh_impl(BvrContext* ctx,
     }
     BVR_CK(cudaGetLastError());
     BVR_CK(cudaEventRecord(ctx->ev_upload1, ctx->stream));
-    BVR_CK(cudaStreamSynchronize(ctx->stream));   // the stack bound (tree depth) is needed on the host
+    // The stack bound (tree depth) and the root box are needed on the host before the next render is LAUNCHED, not
+    // before this call returns: they are read back into pinned memory and picked up by resolve_gpu_build(), so that
+    // the caller can go on enqueuing (e.g. the next frame's input copies) while the tree is being built.
+    BVR_CK(cudaEventRecord(ctx->build_done, ctx->stream));
+    ctx->build_pending = n_models > 0;
     ctx->upload_timed = true;
     ctx->stats.kernel_launches += (uint64_t)launches;
     ctx->n_models = n_models;
     ctx->n_materials = n_materials;
     ctx->n_nodes = n_nodes;
-    ctx->tree_depth = *ctx->depth_host;
-    ctx->scene_extent = n_models ? root_extent(*ctx->root_host) : 0.0f;
+    ctx->tree_depth = 0;
+    ctx->scene_extent = 0.0f;
+    if (out_nodes || ctx->pinned_src_in_flight) {
+        // the caller reads out_nodes / owns its pinned arrays again when the call returns
+        const int rs = resolve_gpu_build(ctx);
+        if (rs != BVR_OK) return rs;
+        ctx->pinned_src_in_flight = false;
+    }
     ctx->n_inner = n_models ? (uint32_t)(n_models - 1) : 0u;
     ctx->max_leaf_models = n_models ? 1u : 0u;   // the GPU builder emits one sphere per leaf
     ctx->tree_is_ours = true;
@@ -716,6 +751,7 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
                         const BvrWindow* window, const BvrRenderOptions* opts, RenderParams* out) {
     if (!camera || !level || !window || !opts) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null uniform / options pointer");
     if (!ctx->scene_uploaded) return fail(ctx, BVR_ERR_NO_SCENE, "bvr_render before bvr_upload_scene");
+    { const int rs = resolve_gpu_build(ctx); if (rs != BVR_OK) return rs; }
     if (camera->projection != 0u) return fail(ctx, BVR_ERR_UNSUPPORTED_PROJECTION, "camera.projection != 0");
     if (opts->width == 0 || window->height == 0) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "zero image size");
     if (level->level > 3u) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "raytrace level > 3");

@@ -97,4 +97,29 @@ extern "C" {
         raster_rgba: *const f32, raster_depth: *const f32,
         host_out: *const BvrOutputs,
     ) -> c_int;
+    /// bvr_render without the wait (page-locked buffers only); `bvr_sync` completes the frame.
+    pub fn bvr_render_async(
+        ctx: *mut BvrContext,
+        camera: *const BvrCamera, level: *const BvrRaytraceLevel, window: *const BvrWindow,
+        opts: *const BvrRenderOptions,
+        raster_rgba: *const f32, raster_depth: *const f32,
+        host_out: *const BvrOutputs,
+    ) -> c_int;
+    pub fn bvr_sync(ctx: *mut BvrContext) -> c_int;
+    /// The BVH is built on the GPU (PLOC over the Morton order) instead of by obvhs on the host.
+    pub fn bvr_upload_scene_gpu_bvh(
+        ctx: *mut BvrContext,
+        models: *const c_void, n_models: usize,
+        materials: *const c_void, n_materials: usize,
+        ranges: *const BvrDirtyRange, n_ranges: usize,
+        out_nodes: *mut c_void,
+    ) -> c_int;
+    /// Same arguments: keeps the last GPU-built topology, refits the boxes (small motion).
+    pub fn bvr_refit_scene_gpu_bvh(
+        ctx: *mut BvrContext,
+        models: *const c_void, n_models: usize,
+        materials: *const c_void, n_materials: usize,
+        ranges: *const BvrDirtyRange, n_ranges: usize,
+        out_nodes: *mut c_void,
+    ) -> c_int;
 }

@@ -103,27 +103,20 @@ def test_dirty_models_rebuild(bvr, ctx, builder):
         ctx.upload_scene_gpu_bvh(models, mats, ranges=[(bvr.capi.ARRAY_BVH_NODES, 0, 1)])
 
 
-def test_ploc_tree_is_deterministic_and_better_than_lbvh(bvr, ctx):
-    """Two PLOC builds of the same models give the same bytes (node ids come from a scan, not from atomics), and the
-    tree is at least as good as the LBVH one by the surface-area heuristic (what PLOC is for)."""
-    for n, seed in ((506, 1), (5000, 2), (60000, 3)):
+def test_ploc_tree_is_deterministic_and_as_good_as_the_host_ploc(bvr, ctx):
+    """Two PLOC builds of the same models give the same bytes (node ids come from a scan, not from atomics), and the tree
+    has the surface-area-heuristic cost of the host PLOC builder's tree (the restated obvhs call, extract.rs:316-321):
+    same algorithm, same search radius, same order.  (On uniformly random spheres a plain LBVH is a few per cent cheaper
+    by that measure; on the structured RTIOW scene PLOC renders faster — profiles/r02_tuning_sweeps.txt.)"""
+    os.environ.pop("BVR_GPU_LBVH", None)
+    ctx.reload_tuning()
+    for n, seed in ((506, 1), (5000, 2), (60000, 3)):      # one CTA / one CTA / cooperative grid
         models, mats = random_models(bvr, n, seed=seed, spread=30.0)
-        os.environ.pop("BVR_GPU_LBVH", None)
-        ctx.reload_tuning()
         a = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
         b = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
         assert a.tobytes() == b.tobytes()
-        os.environ["BVR_GPU_LBVH"] = "1"
-        ctx.reload_tuning()
-        try:
-            lb = ctx.upload_scene_gpu_bvh(models, mats, want_nodes=True)
-        finally:
-            os.environ.pop("BVR_GPU_LBVH", None)
-            ctx.reload_tuning()
-        host = bvr.build_ploc(models)
-        c_ploc, c_lbvh, c_host = sah_cost(a), sah_cost(lb), sah_cost(host)
-        assert c_ploc < c_lbvh, (n, c_ploc, c_lbvh)
-        assert c_ploc < 1.15 * c_host, (n, c_ploc, c_host)      # in the league of the host PLOC (obvhs restatement)
+        c_gpu, c_host = sah_cost(a), sah_cost(bvr.build_ploc(models))
+        assert abs(c_gpu - c_host) < 0.02 * c_host, (n, c_gpu, c_host)
 
 
 def test_refit_keeps_topology_and_matches_the_oracle(bvr, oracle, ctx, builder):
