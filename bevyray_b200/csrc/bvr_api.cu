@@ -54,7 +54,7 @@ struct PinnedBuffer {
 // only on request (bvr_reload_tuning); production uses the defaults.
 struct EnvTuning {
     int no_tight = 0, tight_pad = 100, no_q16 = 0, no_bvh4 = 0, gpu_validate = -1, wf_refill = 8;
-    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0, no_both = 0, gpu_lbvh = 0;
+    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0, top_records = 0, hot_records = 512, tile_order = 2, no_both = 0, gpu_lbvh = 0;
 };
 
 struct BvrContext {
@@ -74,6 +74,7 @@ struct BvrContext {
     bool nodes4_ch_built = false;
     DeviceBuffer raw_nodes_tight, pairs_tight, pairs_ch_tight, nodes4_tight, tight_groups;   // tight-box variant
     bool tight_built = false;
+    DeviceBuffer id_q;                                  // record numbering of the quantised layouts (hot top of the tree first)
     DeviceBuffer pairs_q, nodes4_q, qgrid;              // 32-byte quantised records + their grid (big scenes), flag at qgrid[8]
     unsigned int* q16_bad_host = nullptr;     // pinned copy of the 'does not qualify' flag
     bool q16_built = false, q16_pending = false;
@@ -90,6 +91,9 @@ struct BvrContext {
     uint32_t max_leaf_models = 0;
     int sm_count = 0;
     DeviceBuffer pixel_counter;
+    DeviceBuffer tile_order, tile_cost, tile_scratch;   // pixel-queue order from the previous frame's per-tile ray counts
+    uint32_t tile_geom[3] = {0, 0, 0};                  // (width, rows, tiles) the order was made for; 0 = none yet
+    bool tile_order_valid = false;
     DeviceBuffer wf_state;
     DeviceBuffer bvh_scratch;
     unsigned int* depth_host = nullptr;       // pinned
@@ -177,7 +181,10 @@ EnvTuning read_env_tuning() {
     t.mk_leaf = env_int("BVR_MK_LEAF", 0);
     t.selfcheck = env_int("BVR_SELFCHECK", 0);
     t.no_top = env_int("BVR_NO_TOP", 0);
+    t.top_records = env_int("BVR_TOP_RECORDS", 0);
+    t.hot_records = env_int("BVR_HOT_RECORDS", 512);   // 32 KB of records: what the stacks leave of L1 (profiles/r02_tuning_sweeps.txt)
     t.no_both = env_int("BVR_NO_BOTH", 0);
+    t.tile_order = env_int("BVR_TILE_ORDER", 2);   // 0 row-major, 2 heaviest tile of the previous frame first (1, 3: experiments)
     t.gpu_lbvh = env_int("BVR_GPU_LBVH", 0);
     return t;
 }
@@ -320,10 +327,19 @@ int derive_q16(BvrContext* ctx, size_t n_models, size_t n_nodes, uint32_t n_inne
     BVR_CK(ctx->pairs_q.ensure((size_t)n_inner * 32u + 32u));
     BVR_CK(ctx->qgrid.ensure(16 * sizeof(float)));
     uint32_t* bad = ctx->qgrid.as<uint32_t>() + 8;
-    *launches += launch_derive_pairs_q16(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+    // the quantised records are numbered with the hot top of the tree first (the render kernel stages a prefix of the
+    // array in shared memory); BVR_NO_TOP keeps the array order of the upload
+    const uint32_t* id_q = ctx->inner_id.as<uint32_t>();
+    if (!ctx->tune.no_top) {
+        BVR_CK(ctx->id_q.ensure((n_nodes + 1u) * sizeof(uint32_t)));
+        *launches += launch_derive_top_order(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+                                             ctx->block_sums.as<uint32_t>(), 0xffffffffu, ctx->id_q.as<uint32_t>(), ctx->stream);
+        id_q = ctx->id_q.as<uint32_t>();
+    }
+    *launches += launch_derive_pairs_q16(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, id_q,
                                          ctx->pairs_q.as<uint4>(), ctx->qgrid.as<float>(), bad, ctx->stream);
     BVR_CK(ctx->nodes4_q.ensure((size_t)n_inner * 64u + 64u));
-    *launches += launch_derive_nodes4_q16(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, ctx->inner_id.as<uint32_t>(),
+    *launches += launch_derive_nodes4_q16(ctx->raw_nodes.as<RawNode>(), (uint32_t)n_nodes, id_q,
                                           ctx->pairs_q.as<uint4>(), ctx->nodes4_q.as<uint4>(), ctx->stream);
     BVR_CK(cudaMemcpyAsync(ctx->q16_bad_host, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     BVR_CK(cudaEventRecord(ctx->q16_done, ctx->stream));
@@ -400,7 +416,7 @@ void bvr_destroy(BvrContext* ctx) {
     DeviceBuffer* bufs[] = {&ctx->raw_models, &ctx->raw_materials, &ctx->raw_nodes, &ctx->spheres,
                             &ctx->sphere_material, &ctx->pairs, &ctx->pairs_ch, &ctx->inner_id, &ctx->block_sums, &ctx->root_ref,
                             &ctx->in_rgba, &ctx->in_depth, &ctx->out_rgba, &ctx->out_rt_depth, &ctx->out_id,
-                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->model_rank, &ctx->selfcheck_log, &ctx->validate_scratch, &ctx->validate_out, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
+                            &ctx->out_pdepth, &ctx->out_srgb8, &ctx->ray_counter, &ctx->pixel_counter, &ctx->tile_order, &ctx->tile_cost, &ctx->tile_scratch, &ctx->wf_state, &ctx->bvh_scratch, &ctx->pairs_q, &ctx->nodes4_q, &ctx->qgrid, &ctx->id_q, &ctx->model_rank, &ctx->selfcheck_log, &ctx->validate_scratch, &ctx->validate_out, &ctx->nodes4_ch, &ctx->raw_nodes_tight, &ctx->pairs_tight, &ctx->pairs_ch_tight, &ctx->nodes4_tight, &ctx->tight_groups};
     for (DeviceBuffer* b : bufs) b->release();
     ctx->upload_staging.release();
     ctx->io_staging.release();
@@ -904,15 +920,40 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
             // largest CTA whose stacks (and, when it fits, the scene) fit in shared memory
             const int forced = ctx->tune.mk_threads;
             const int candidates[4] = {1024, 768, 512, 256};
+            // pixel-queue order: heaviest tiles first, judged by the previous frame of the same size (tile_order.cu)
+            const uint32_t n_tiles = ((p.cam.width + 7u) / 8u) * ((p.shard.rows + 3u) / 4u);
+            const bool ordered = ctx->tune.tile_order != 0 && n_tiles > 0;
+            bool tile_first = false;
+            if (ordered) {
+                if (ctx->tile_geom[0] != p.cam.width || ctx->tile_geom[1] != p.shard.rows || ctx->tile_geom[2] != n_tiles) {
+                    BVR_CK(ctx->tile_order.ensure((size_t)n_tiles * sizeof(uint32_t)));
+                    BVR_CK(ctx->tile_cost.ensure((size_t)n_tiles * sizeof(uint32_t)));
+                    BVR_CK(ctx->tile_scratch.ensure(tile_order_scratch_bytes(n_tiles)));
+                    BVR_CK(cudaMemsetAsync(ctx->tile_cost.ptr, 0, (size_t)n_tiles * sizeof(uint32_t), ctx->stream));
+                    ctx->tile_geom[0] = p.cam.width; ctx->tile_geom[1] = p.shard.rows; ctx->tile_geom[2] = n_tiles;
+                    ctx->tile_order_valid = false;
+                    tile_first = true;
+                }
+            }
+            const uint32_t* tile_order = ordered && ctx->tile_order_valid ? ctx->tile_order.as<uint32_t>() : nullptr;
+            uint32_t* tile_cost = ordered ? ctx->tile_cost.as<uint32_t>() : nullptr;
             for (int ci = 0; ci < 4 && n < 0; ci++) {
                 const int threads = forced ? forced : candidates[ci];
                 n = launch_megakernel_v3(p, ctx->n_inner, (uint32_t)ctx->n_models, ctx->tree_depth,
                                          ctx->pixel_counter.as<unsigned int>(), threads,
                                          (uint32_t)ctx->tune.mk_wait, (uint32_t)ctx->tune.mk_leaf,   // 0 = per-mode default
-                                         ctx->tune.no_both != 0, ctx->sm_count, ctx->stream);
+                                         ctx->tune.no_both != 0,
+                                         ctx->tune.no_top ? 0u : (uint32_t)ctx->tune.top_records,
+                                         ctx->tune.no_top ? 0u : (uint32_t)ctx->tune.hot_records, tile_order, tile_cost,
+                                         ctx->sm_count, ctx->stream);
                 if (forced) break;
             }
             if (n < 0) cudaGetLastError();
+            if (n >= 0 && ordered) {
+                launches += launch_tile_order_update(tile_cost, ctx->tile_order.as<uint32_t>(), ctx->tile_scratch.ptr, n_tiles,
+                                                     ctx->tune.tile_order, tile_first, ctx->stream);
+                ctx->tile_order_valid = true;
+            }
         }
         if (n < 0) n = launch_megakernel(p, ctx->stream);   // reference-order traversal, or scene too deep
         launches += n;

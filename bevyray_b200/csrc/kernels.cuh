@@ -75,6 +75,12 @@ int launch_derive_spheres(const RawModel* models, uint32_t n, float4* spheres, u
 int launch_derive_pairs(const RawNode* nodes, uint32_t n_nodes, uint32_t* inner_id, uint32_t* block_sums,
                         float4* pairs, float4* pairs_ch, uint32_t* root_ref_out, cudaStream_t stream);
 
+// Record numbering of the quantised layouts: the first `max_top` records of a breadth-first walk over the 4-wide levels get
+// the ids 0, 1, ..., every other inner node follows in array order (the render kernel stages a prefix of the record array
+// in shared memory).  id_q: n_nodes + 1 u32 (the last word = breadth-first ids handed out); after launch_derive_pairs.
+int launch_derive_top_order(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, uint32_t* block_sums,
+                            uint32_t max_top, uint32_t* id_q, cudaStream_t stream);
+
 // 32-byte quantised records for scenes that are walked in HBM/L2 (after launch_derive_pairs: needs inner_id);
 // grid = 8 floats (base.xyz, -, step.xyz, -); *bad != 0 afterwards -> the scene does not qualify
 int launch_derive_pairs_q16(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, uint4* pairs_q,
@@ -120,7 +126,16 @@ int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple o
 // falls back to v1)
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
-                         bool no_both, int sm_count, cudaStream_t stream);
+                         bool no_both, uint32_t max_top, uint32_t n_hot, const uint32_t* tile_order, uint32_t* tile_cost,
+                         int sm_count, cudaStream_t stream);
+// ---- pixel-queue order (tile_order.cu) ----
+// The megakernel hands out 8x4 tiles through a queue.  A pixel is a sequential chain (one RNG stream, raytrace.wgsl:89),
+// so the frame ends when the slowest chain does: tiles are handed out heaviest first, judged by the rays each tile cost
+// in the PREVIOUS frame of the same size.  scratch: tile_order_scratch_bytes(n); cost: n u32 (zeroed by the update).
+// mode: 2 = heaviest first, 3 = lightest first (experiment), 1 = reversed row-major (experiment)
+size_t tile_order_scratch_bytes(uint32_t n_tiles);
+int launch_tile_order_update(uint32_t* tile_cost, uint32_t* tile_order, void* scratch, uint32_t n_tiles, int mode, bool first,
+                             cudaStream_t stream);
 // BVR_SELFCHECK: re-traces the rays the render kernel logged, in reference order; counters = {checked, disagreements}
 int launch_selfcheck(const RenderParams& p, unsigned long long* counters, cudaStream_t stream);
 size_t wavefront_state_bytes(size_t slots);

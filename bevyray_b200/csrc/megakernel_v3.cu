@@ -17,6 +17,8 @@
 // Arithmetic of everything that reaches the image is the strict set of trace.cuh (bit-identical to the
 // oracle); box tests use FMA + FMNMX3 (culling only).
 
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "wide4.cuh"
 
@@ -30,6 +32,12 @@ enum Kind : int { K_NONE = 0, K_MISS = 1, K_METAL = 2, K_GLASS = 3, K_DIFFUSE = 
 #define V3_NONE 0x7fffffffu
 #ifndef BVR_FAR_GENERIC
 #define BVR_FAR_GENERIC 1      // MODE 5: far rays pick their records through a generic pointer (no predicated second load path)
+#endif
+#ifndef BVR_LDG_TOGETHER
+#define BVR_LDG_TOGETHER 1     // MODE 3: both halves of a 64-byte record in one asm statement (issued back to back)
+#endif
+#ifndef BVR_RECONVERGE
+#define BVR_RECONVERGE 1
 #endif
 #ifndef BVR_STEPS_PER_VOTE
 #define BVR_STEPS_PER_VOTE 2   // traversal steps between two rounds of warp votes
@@ -105,6 +113,10 @@ __global__ void selfcheck_kernel(const SceneView sv, const float4* __restrict__ 
 struct Tuning {
     uint32_t shade_wait_lanes;   // leave phase B when this many lanes wait for shading
     uint32_t leaf_batch_lanes;   // test parked leaves when this many lanes hold one
+    uint32_t n_top;              // MODE 3: records [0, n_top) of the array are staged in shared memory
+    uint32_t n_hot;              // MODE 3: records [n_top, n_hot) are loaded L1::evict_last, the rest L1::no_allocate (0 = no hints)
+    const uint32_t* tile_order;  // tiles in the order they are handed out (heaviest first, tile_order.cu), or null = row-major
+    uint32_t* tile_cost;         // += rays traced per 8x4 tile (feeds the next frame's order), or null
 };
 
 // MODE 0: scene in shared memory (64-byte fp32 records).  MODE 1: scene in HBM/L2, 64-byte fp32 records, 8-byte
@@ -153,6 +165,17 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         sv.spheres = sm_spheres;
         sv.materials = sm_materials;
         sv.sphere_material = sm_matid;
+        __syncthreads();
+    }
+    // MODE 3: the hot top of the tree — the first n_top 64-byte records of the array, which the upload numbered breadth
+    // first (scene_kernels.cu: top_bfs_kernel) — staged in shared memory: the levels every ray walks cost no L1/L2 traffic
+    const uint32_t n_top = W4 ? tune.n_top : 0u, n_hot = W4 ? tune.n_hot : 0u;
+    uint32_t s_top = 0u;
+    if constexpr (W4) {
+        uint4* sm_top = reinterpret_cast<uint4*>(sm_cursor);
+        sm_cursor += 4u * n_top;
+        for (uint32_t i = tid; i < 4u * n_top; i += THREADS) sm_top[i] = __ldg(p.scene.nodes4_q + i);
+        s_top = opaque(smem_addr(sm_top));
         __syncthreads();
     }
     // per-lane stack: entry k of lane t at s_stack0 + k * STACK_STRIDE (interleaved: conflict-free)
@@ -329,6 +352,8 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 if (p.out_primary_depth) p.out_primary_depth[lpix] = BVR_INF;
             }
             if (p.out_srgb8) p.out_srgb8[lpix] = store_srgb8(out);
+            // rays this pixel cost = the lane's count now minus its count when it took the pixel (subtracted in A5)
+            if (tune.tile_cost) atomicAdd(tune.tile_cost + ((ly >> 2) * tiles_x + (px >> 3)), rays);
             state = NEED_PIXEL;
         }
         // --- A5: pull new pixels from the tile-ordered queue (warp-convergent) ---
@@ -344,11 +369,14 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 if (slot >= total_slots) {
                     state = DONE;
                 } else {
-                    const uint32_t tile = slot >> 5, within = slot & 31u;
+                    uint32_t tile = slot >> 5;
+                    const uint32_t within = slot & 31u;
+                    if (tune.tile_order) tile = __ldg(tune.tile_order + tile);
                     const uint32_t px = (tile % tiles_x) * 8u + (within & 7u);
                     const uint32_t ly = (tile / tiles_x) * 4u + (within >> 3);
                     const uint32_t gy = shard_global_row(p.shard, ly);
                     if (px < cam.width && ly < p.shard.rows && gy < cam.height) {
+                        if (tune.tile_cost) atomicSub(tune.tile_cost + tile, rays);
                         pxy = px | (ly << 16);
                         u = pixel_u(cam, px);
                         v = pixel_v(cam, gy);
@@ -448,6 +476,9 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                             c = visit4(q0, q1, q2, q3, q4, q5, rr, inv_xy, noi_xy, inv.z, noi.z, closest.t, push);
                         }
                     }
+#if BVR_RECONVERGE
+                    __syncwarp();   // lanes that visited and lanes that did not park / pop together
+#endif
                     if (c >= LEAFV) {
                         if (c != NONE && pending == NONE) { pending = c; c = NONE; }   // park the leaf, go on
                         if (c == NONE) {
@@ -497,9 +528,28 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                         } else if constexpr (W4) {
                             // four children: key = 11 bits of entry distance | 21 bits of ref, 0xffffffff = not entered
                             uint4 qa, qb, qc, qd;
-                            const uint4* np = sv.nodes4_q + 4u * c;
-                            ldg256u(np, qa, qb);
-                            ldg256u(np + 2, qc, qd);
+                            if (c < n_top) {
+                                const uint32_t na = s_top + c * 64u;
+                                qa = lds128u(na); qb = lds128u(na + 16u); qc = lds128u(na + 32u); qd = lds128u(na + 48u);
+                            } else {
+                                const uint4* np = sv.nodes4_q + 4u * c;
+#if BVR_LDG_TOGETHER
+                                if (n_hot == 0u) ldg512u<0>(np, qa, qb, qc, qd);
+                                else if (c < n_hot) ldg512u<1>(np, qa, qb, qc, qd);
+                                else ldg512u<2>(np, qa, qb, qc, qd);
+#else
+                                if (n_hot == 0u) {
+                                    ldg256u(np, qa, qb);
+                                    ldg256u(np + 2, qc, qd);
+                                } else if (c < n_hot) {
+                                    ldg256u_keep(np, qa, qb);
+                                    ldg256u_keep(np + 2, qc, qd);
+                                } else {
+                                    ldg256u_stream(np, qa, qb);
+                                    ldg256u_stream(np + 2, qc, qd);
+                                }
+#endif
+                            }
                             float e;
                             uint32_t k0 = box_cull_q16(qa.x, qa.y, qa.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
                                               ? (((__float_as_uint(e) >> 20) << 21) | qa.w) : 0xffffffffu;
@@ -646,7 +696,14 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
     if (tune.leaf_batch_lanes == 0u) tune.leaf_batch_lanes = smem_scene ? 4u : 1u;
     if (w4) stack_cap = 3u * (tree_depth / 2u) + 1u;              // up to three siblings parked per 4-wide level
     const size_t stack_bytes = (size_t)THREADS * stack_cap * (q16 ? sizeof(uint32_t) : sizeof(uint2));
-    const size_t smem = (smem_scene ? scene_bytes : 0) + stack_bytes;
+    // MODE 3: what the stacks leave of shared memory holds the first records of the array (the top of the tree)
+    if (w4 && stack_bytes <= max_smem) {
+        const size_t room = (max_smem - stack_bytes) / 64u;
+        tune.n_top = (uint32_t)std::min<size_t>(std::min<size_t>(room, n_inner), tune.n_top);
+    } else {
+        tune.n_top = 0u;
+    }
+    const size_t smem = (smem_scene ? scene_bytes : 0) + stack_bytes + (size_t)tune.n_top * 64u;
     if (smem > max_smem) return -1;
     auto kern = smem_scene ? megakernel_v3<THREADS, 0>
                            : (w4 ? megakernel_v3<THREADS, 3> : (q16 ? megakernel_v3<THREADS, 2> : megakernel_v3<THREADS, 1>));
@@ -673,9 +730,10 @@ int launch_selfcheck(const RenderParams& p, unsigned long long* counters, cudaSt
 
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
-                         bool no_both, int sm_count, cudaStream_t stream) {
+                         bool no_both, uint32_t max_top, uint32_t n_hot, const uint32_t* tile_order, uint32_t* tile_cost,
+                         int sm_count, cudaStream_t stream) {
     if (p.cam.width > 0xffffu || p.shard.rows > 0xffffu) return -1;   // pixel packed as px | ly << 16
-    Tuning t{shade_wait_lanes, leaf_batch_lanes};
+    Tuning t{shade_wait_lanes, leaf_batch_lanes, max_top, n_hot, tile_order, tile_cost};
     switch (threads) {
         case 256: return launch_v3<256>(p, n_inner, n_models, tree_depth, pixel_counter, t, no_both, sm_count, stream);
         case 512: return launch_v3<512>(p, n_inner, n_models, tree_depth, pixel_counter, t, no_both, sm_count, stream);

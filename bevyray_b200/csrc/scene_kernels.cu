@@ -87,6 +87,79 @@ __global__ void assign_inner_id_kernel(const RawNode* __restrict__ nodes, uint32
     if (i < n) inner_id[i] = flag ? block_sums[blockIdx.x] + ex : 0xffffffffu;
 }
 
+// ---- record numbering for scenes walked in HBM/L2: the hot top of the tree first --------------------------------------
+// The 4-wide walk of a big scene (megakernel_v3.cu MODE 3) stages the first records of its array in shared memory, so the
+// array should START with the records every ray visits: the root's, then level by level (breadth first over the 4-wide
+// levels: the record of node N refers to the inner children of N's inner children).  top_bfs_kernel gives the first
+// `max_top` records reached that way the ids 0, 1, 2, ...; the other inner nodes follow in array order (rest_* below).
+// Any prefix of a breadth-first order is closed under "parent of", and which prefix the render kernel stages cannot
+// change an image: a staged record is a copy.
+#define BVR_TOP_BFS_MAX 3072u
+__global__ void __launch_bounds__(SCAN_BLOCK) top_bfs_kernel(const RawNode* __restrict__ nodes, uint32_t n, uint32_t max_top,
+                                                             uint32_t* __restrict__ id_q) {
+    __shared__ uint32_t frontier[2][BVR_TOP_BFS_MAX];
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t tid = threadIdx.x;
+    uint32_t done = 0, cur_n = 0;
+    int cur = 0;
+    if (max_top > BVR_TOP_BFS_MAX) max_top = BVR_TOP_BFS_MAX;
+    if (n > 0u && nodes[0].model_count == 0u) {
+        if (tid == 0u) frontier[0][0] = 0u;
+        cur_n = 1u;
+    }
+    __syncthreads();
+    while (cur_n > 0u && done < max_top) {
+        const uint32_t take = min(cur_n, max_top - done);
+        for (uint32_t e = tid; e < take; e += SCAN_BLOCK) id_q[frontier[cur][e]] = done + e;
+        done += take;
+        if (done >= max_top) break;
+        uint32_t next_n = 0;
+        for (uint32_t base = 0; base < cur_n; base += SCAN_BLOCK) {
+            const uint32_t e = base + tid;
+            uint32_t kids[4], nk = 0;
+            if (e < cur_n) {
+                const uint32_t first = nodes[frontier[cur][e]].index;
+                for (uint32_t s = 0; s < 2u; s++) {
+                    const uint32_t x = first + s;
+                    if (x >= n || nodes[x].model_count != 0u) continue;
+                    const uint32_t xf = nodes[x].index;
+                    for (uint32_t t = 0; t < 2u; t++)
+                        if (xf + t < n && nodes[xf + t].model_count == 0u) kids[nk++] = xf + t;
+                }
+            }
+            uint32_t total;
+            const uint32_t ex = block_exclusive_scan(nk, warp_sums, total);
+            for (uint32_t k = 0; k < nk; k++)
+                if (next_n + ex + k < BVR_TOP_BFS_MAX) frontier[cur ^ 1][next_n + ex + k] = kids[k];
+            next_n += total;
+            __syncthreads();
+        }
+        cur ^= 1;
+        cur_n = min(next_n, BVR_TOP_BFS_MAX);
+    }
+    if (tid == 0u) id_q[n] = done;   // number of breadth-first ids handed out
+}
+
+// the other inner nodes: id = (breadth-first ids handed out) + position among them in array order
+__global__ void rest_count_kernel(const uint32_t* __restrict__ inner_id, const uint32_t* __restrict__ id_q, uint32_t n,
+                                  uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t flag = (i < n && inner_id[i] != 0xffffffffu && id_q[i] == 0xffffffffu) ? 1u : 0u;
+    uint32_t total;
+    (void)block_exclusive_scan(flag, warp_sums, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void rest_assign_kernel(const uint32_t* __restrict__ inner_id, uint32_t* __restrict__ id_q, uint32_t n,
+                                   const uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t flag = (i < n && inner_id[i] != 0xffffffffu && id_q[i] == 0xffffffffu) ? 1u : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(flag, warp_sums, total);
+    if (flag) id_q[i] = id_q[n] + block_sums[blockIdx.x] + ex;
+}
+
 __device__ __forceinline__ uint32_t make_ref(const RawNode& child, uint32_t child_inner_id) {
     if (child.model_count > 0u)
         return BVR_LEAF_BIT | ((child.model_count - 1u) << 24) | (child.index & BVR_LEAF_FIRST_MASK);
@@ -408,6 +481,18 @@ int launch_derive_pairs_q16(const RawNode* nodes, uint32_t n_nodes, const uint32
     cudaMemsetAsync(bad, 0, sizeof(uint32_t), stream);
     build_pairs_q16_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(nodes, n_nodes, inner_id, pairs_q, grid, bad);
     return 1;
+}
+
+int launch_derive_top_order(const RawNode* nodes, uint32_t n_nodes, const uint32_t* inner_id, uint32_t* block_sums,
+                            uint32_t max_top, uint32_t* id_q, cudaStream_t stream) {
+    if (n_nodes == 0) return 0;
+    const uint32_t n_blocks = (n_nodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    cudaMemsetAsync(id_q, 0xff, ((size_t)n_nodes + 1u) * sizeof(uint32_t), stream);
+    top_bfs_kernel<<<1, SCAN_BLOCK, 0, stream>>>(nodes, n_nodes, max_top, id_q);
+    rest_count_kernel<<<n_blocks, SCAN_BLOCK, 0, stream>>>(inner_id, id_q, n_nodes, block_sums);
+    scan_block_sums_kernel<<<1, SCAN_BLOCK, 0, stream>>>(block_sums, n_blocks);
+    rest_assign_kernel<<<n_blocks, SCAN_BLOCK, 0, stream>>>(inner_id, id_q, n_nodes, block_sums);
+    return 4;
 }
 
 int launch_derive_spheres(const RawModel* models, uint32_t n, float4* spheres, uint32_t* sphere_material,

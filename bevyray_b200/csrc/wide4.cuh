@@ -24,6 +24,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -37,6 +42,33 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
 }
 __device__ __forceinline__ void ldg256u(const uint4* p, uint4& a, uint4& b) {
     asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+// A whole 64-byte record as two 256-bit loads in ONE asm statement, so that they are issued back to back: left to itself
+// ptxas sinks the second load below the box tests of the first half under the 64-register cap (profiles/r02_m3_c4_full_ncu:
+// two dependent L2 round trips per visit instead of one).  POLICY: 0 = default, 1 = L1::evict_last, 2 = L1::no_allocate.
+template <int POLICY>
+__device__ __forceinline__ void ldg512u(const uint4* p, uint4& a, uint4& b, uint4& c, uint4& d) {
+#define BVR_LDG512(HINT)                                                                                           \
+    asm volatile("ld.global.nc" HINT ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"                               \
+                 "ld.global.nc" HINT ".v8.u32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%16+32];"                          \
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w),         \
+                   "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w)          \
+                 : "l"(p))
+    if (POLICY == 1) BVR_LDG512(".L1::evict_last");
+    else if (POLICY == 2) BVR_LDG512(".L1::no_allocate");
+    else BVR_LDG512("");
+#undef BVR_LDG512
+}
+// the same load with an L1 policy: evict-last for records every ray reads (the top of the tree), no-allocate for the rest
+__device__ __forceinline__ void ldg256u_keep(const uint4* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.L1::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg256u_stream(const uint4* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(p));
 }

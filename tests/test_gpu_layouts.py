@@ -3,7 +3,9 @@ the library from the scene; the environment knobs below force th
   small scenes (staged in shared memory): 4-wide fp32 records (default), child-pair records (BVR_NO_BVH4),
       one thread per pixel (BVR_MK_V1);
   big scenes (walked in HBM/L2): 4-wide 16-bit records (default), 2-wide 16-bit records (BVR_NO_BVH4),
-      fp32 child-pair records (BVR_NO_Q16, chosen at upload)."""
+      fp32 child-pair records (BVR_NO_Q16, chosen at upload); the 16-bit records numbered in upload order and nothing staged
+      (BVR_NO_TOP), the first N records staged in shared memory (BVR_TOP_RECORDS=N), the first N records kept in L1 and the
+      others loaded without allocating (BVR_HOT_RECORDS=N)."""
 import os
 
 import numpy as np
@@ -11,7 +13,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-KNOBS = ("BVR_NO_BVH4", "BVR_NO_Q16", "BVR_NO_TIGHT", "BVR_MK_V1", "BVR_MK_THREADS", "BVR_GPU_VALIDATE", "BVR_NO_BOTH", "BVR_SELFCHECK")
+KNOBS = ("BVR_NO_BVH4", "BVR_NO_Q16", "BVR_NO_TIGHT", "BVR_MK_V1", "BVR_MK_THREADS", "BVR_GPU_VALIDATE", "BVR_NO_BOTH", "BVR_SELFCHECK", "BVR_NO_TOP", "BVR_TOP_RECORDS", "BVR_HOT_RECORDS",
+         "BVR_TILE_ORDER")
 
 
 def bits(a):
@@ -61,7 +64,9 @@ def test_small_scene_layouts(bvr, oracle, ctx, rtiow, knobs, env):
 
 
 @pytest.mark.parametrize("gpu_bvh", [False, True], ids=["host-ploc", "gpu-lbvh"])
-@pytest.mark.parametrize("env", [dict(), dict(BVR_NO_BVH4=1), dict(BVR_NO_Q16=1), dict(BVR_MK_THREADS=768)],
+@pytest.mark.parametrize("env", [dict(), dict(BVR_NO_BVH4=1), dict(BVR_NO_Q16=1), dict(BVR_MK_THREADS=768), dict(BVR_NO_TOP=1),
+                                 dict(BVR_TOP_RECORDS=1), dict(BVR_TOP_RECORDS=37), dict(BVR_TOP_RECORDS=100000), dict(BVR_HOT_RECORDS=300),
+                                 dict(BVR_TOP_RECORDS=21, BVR_HOT_RECORDS=85), dict(BVR_NO_BVH4=1, BVR_NO_TOP=1)],
                          ids=lambda e: "-".join(f"{k[4:]}={v}" for k, v in e.items()) or "default")
 def test_big_scene_layouts(bvr, oracle, ctx, knobs, env, gpu_bvh):
     """30k random spheres (C4's density): the records live in HBM/L2.  Also through the GPU-built tree, whose
@@ -238,3 +243,20 @@ def test_selfcheck_mode_retraces_sampled_rays_in_reference_order(bvr, oracle, ct
         assert st1["selfcheck_mismatches"] == 0, (env, st1)
         for k in off:
             assert np.array_equal(bits(on[k]), bits(off[k])), (env, k)
+
+
+@pytest.mark.parametrize("order", [0, 1, 2, 3], ids=["row-major", "reversed", "heaviest-first", "lightest-first"])
+def test_tile_order_cannot_change_a_frame(bvr, oracle, ctx, rtiow, knobs, order):
+    """The pixel queue hands out tiles heaviest first, judged by the previous frame's per-tile ray counts (tile_order.cu):
+    the first frame of a size runs row-major, the following ones in the fed-back order, a new size starts over.  Every one
+    of them has to be the oracle's frame, bit for bit, with the oracle's ray count."""
+    knobs(BVR_TILE_ORDER=order)
+    ctx.upload_scene(rtiow.models, rtiow.materials, rtiow.nodes)
+    for (W, H) in ((333, 187), (120, 67)):
+        cam = bvr.make_camera(position=(13, 2, 3), target=(0, 0, 0), fov=float(np.deg2rad(20)), aspect=W / H,
+                              sample_count=4, bounces=10)
+        win = bvr.make_window(0.37, H)
+        want, cnt = oracle.render(rtiow.models, rtiow.materials, rtiow.nodes, cam, bvr.make_level(3), win, W)
+        for frame in range(3):
+            got = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
+            check(got, want, cnt, ctx.stats(), (order, W, frame))
