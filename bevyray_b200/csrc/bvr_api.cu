@@ -54,7 +54,7 @@ struct PinnedBuffer {
 // only on request (bvr_reload_tuning); production uses the defaults.
 struct EnvTuning {
     int no_tight = 0, tight_pad = 100, no_q16 = 0, no_bvh4 = 0, gpu_validate = -1, wf_refill = 8;
-    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0, top_records = 0, hot_records = 512, tile_order = 2, no_both = 0, gpu_lbvh = 0;
+    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0, top_records = 0, hot_records = 512, w4_lean = 0, tile_order = -1, no_both = 0, gpu_lbvh = 0;
 };
 
 struct BvrContext {
@@ -92,7 +92,7 @@ struct BvrContext {
     int sm_count = 0;
     DeviceBuffer pixel_counter;
     DeviceBuffer tile_order, tile_cost, tile_scratch;   // pixel-queue order from the previous frame's per-tile ray counts
-    uint32_t tile_geom[3] = {0, 0, 0};                  // (width, rows, tiles) the order was made for; 0 = none yet
+    uint32_t tile_geom[4] = {0, 0, 0, 0};               // (width, rows, tiles, mode) the order was made for; 0 = none yet
     bool tile_order_valid = false;
     DeviceBuffer wf_state;
     DeviceBuffer bvh_scratch;
@@ -182,9 +182,12 @@ EnvTuning read_env_tuning() {
     t.selfcheck = env_int("BVR_SELFCHECK", 0);
     t.no_top = env_int("BVR_NO_TOP", 0);
     t.top_records = env_int("BVR_TOP_RECORDS", 0);
+    t.w4_lean = env_int("BVR_W4_LEAN", 0);
     t.hot_records = env_int("BVR_HOT_RECORDS", 512);   // 32 KB of records: what the stacks leave of L1 (profiles/r02_tuning_sweeps.txt)
     t.no_both = env_int("BVR_NO_BOTH", 0);
-    t.tile_order = env_int("BVR_TILE_ORDER", 2);   // 0 row-major, 2 heaviest tile of the previous frame first (1, 3: experiments)
+    // -1 (default): heaviest tile of the previous frame first when the frame is big enough to repay the sort;
+    // 0 row-major, 2 heaviest first whatever the size (1, 3: experiments — reversed row-major, lightest first)
+    t.tile_order = env_int("BVR_TILE_ORDER", -1);
     t.gpu_lbvh = env_int("BVR_GPU_LBVH", 0);
     return t;
 }
@@ -922,15 +925,20 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
             const int candidates[4] = {1024, 768, 512, 256};
             // pixel-queue order: heaviest tiles first, judged by the previous frame of the same size (tile_order.cu)
             const uint32_t n_tiles = ((p.cam.width + 7u) / 8u) * ((p.shard.rows + 3u) / 4u);
-            const bool ordered = ctx->tune.tile_order != 0 && n_tiles > 0;
+            // (the sort costs ~40 us per frame: worth it from about 2^24 pixel samples, i.e. frames of a few milliseconds)
+            const int order_mode = ctx->tune.tile_order >= 0 ? ctx->tune.tile_order
+                                   : ((uint64_t)n_tiles * 32u * p.cam.sample_count >= (1ull << 24) ? 2 : 0);
+            const bool ordered = order_mode != 0 && n_tiles > 0;
             bool tile_first = false;
             if (ordered) {
-                if (ctx->tile_geom[0] != p.cam.width || ctx->tile_geom[1] != p.shard.rows || ctx->tile_geom[2] != n_tiles) {
+                if (ctx->tile_geom[0] != p.cam.width || ctx->tile_geom[1] != p.shard.rows || ctx->tile_geom[2] != n_tiles ||
+                    ctx->tile_geom[3] != (uint32_t)order_mode) {
                     BVR_CK(ctx->tile_order.ensure((size_t)n_tiles * sizeof(uint32_t)));
                     BVR_CK(ctx->tile_cost.ensure((size_t)n_tiles * sizeof(uint32_t)));
                     BVR_CK(ctx->tile_scratch.ensure(tile_order_scratch_bytes(n_tiles)));
                     BVR_CK(cudaMemsetAsync(ctx->tile_cost.ptr, 0, (size_t)n_tiles * sizeof(uint32_t), ctx->stream));
                     ctx->tile_geom[0] = p.cam.width; ctx->tile_geom[1] = p.shard.rows; ctx->tile_geom[2] = n_tiles;
+                    ctx->tile_geom[3] = (uint32_t)order_mode;
                     ctx->tile_order_valid = false;
                     tile_first = true;
                 }
@@ -944,14 +952,15 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
                                          (uint32_t)ctx->tune.mk_wait, (uint32_t)ctx->tune.mk_leaf,   // 0 = per-mode default
                                          ctx->tune.no_both != 0,
                                          ctx->tune.no_top ? 0u : (uint32_t)ctx->tune.top_records,
-                                         ctx->tune.no_top ? 0u : (uint32_t)ctx->tune.hot_records, tile_order, tile_cost,
+                                         ctx->tune.no_top ? 0u : (uint32_t)ctx->tune.hot_records, ctx->tune.w4_lean != 0,
+                                         tile_order, tile_cost,
                                          ctx->sm_count, ctx->stream);
                 if (forced) break;
             }
             if (n < 0) cudaGetLastError();
             if (n >= 0 && ordered) {
                 launches += launch_tile_order_update(tile_cost, ctx->tile_order.as<uint32_t>(), ctx->tile_scratch.ptr, n_tiles,
-                                                     ctx->tune.tile_order, tile_first, ctx->stream);
+                                                     order_mode, tile_first, ctx->stream);
                 ctx->tile_order_valid = true;
             }
         }

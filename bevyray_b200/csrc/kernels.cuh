@@ -126,8 +126,8 @@ int launch_megakernel(const RenderParams& p, cudaStream_t stream);   // simple o
 // falls back to v1)
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
-                         bool no_both, uint32_t max_top, uint32_t n_hot, const uint32_t* tile_order, uint32_t* tile_cost,
-                         int sm_count, cudaStream_t stream);
+                         bool no_both, uint32_t max_top, uint32_t n_hot, bool lean_w4, const uint32_t* tile_order,
+                         uint32_t* tile_cost, int sm_count, cudaStream_t stream);
 // ---- pixel-queue order (tile_order.cu) ----
 // The megakernel hands out 8x4 tiles through a queue.  A pixel is a sequential chain (one RNG stream, raytrace.wgsl:89),
 // so the frame ends when the slowest chain does: tiles are handed out heaviest first, judged by the rays each tile cost

@@ -115,6 +115,7 @@ struct Tuning {
     uint32_t leaf_batch_lanes;   // test parked leaves when this many lanes hold one
     uint32_t n_top;              // MODE 3: records [0, n_top) of the array are staged in shared memory
     uint32_t n_hot;              // MODE 3: records [n_top, n_hot) are loaded L1::evict_last, the rest L1::no_allocate (0 = no hints)
+    uint32_t lean_w4;            // MODE 3 -> MODE 7: the (cur, pending, stack) loop on the 16-bit-grid records
     const uint32_t* tile_order;  // tiles in the order they are handed out (heaviest first, tile_order.cu), or null = row-major
     uint32_t* tile_cost;         // += rays traced per 8x4 tile (feeds the next frame's order), or null
 };
@@ -135,8 +136,9 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     constexpr bool SMEM_SCENE = MODE == 0 || MODE == 4 || MODE == 5 || MODE == 6;
     constexpr bool TIGHT = MODE == 5 || MODE == 6;
     constexpr bool BOTH = MODE == 6;          // tight AND reference records staged in shared memory
-    constexpr bool Q16 = MODE == 2 || MODE == 3;
-    constexpr bool W4 = MODE == 3;
+    constexpr bool Q16 = MODE == 2 || MODE == 3 || MODE == 7;
+    constexpr bool W4 = MODE == 3 || MODE == 7;
+    constexpr bool LEAN = MODE == 4 || MODE == 5 || MODE == 6 || MODE == 7;   // the (cur, pending, stack) traversal loop
     constexpr bool S4 = MODE == 4 || MODE == 5 || MODE == 6;
     constexpr bool STACK4 = Q16 || S4;        // 4-byte stack entries
     constexpr uint32_t NONE = Q16 ? Q16_NONE : (S4 ? S4_NONE : V3_NONE);
@@ -440,8 +442,9 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         }
 
         // ======================= phase B: traversal =======================
-        if constexpr (S4) {
-            // 4-wide records staged in shared memory.  A lane's traversal state IS (cur, pending, stack):
+        if constexpr (LEAN) {
+            // 4-wide records (staged in shared memory: S4; 16-bit-grid records in HBM/L2: MODE 7).  A lane's traversal state IS
+            // (cur, pending, stack):
             //   cur < LEAFV inner record to visit, LEAFV <= cur < NONE a leaf, NONE nothing in hand;
             //   pending = a parked leaf (tested with the others' once a lane cannot go on without its test).
             // A lane with nothing in hand, nothing parked and an empty stack is idle: its ray is finished (or it has
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             // (The 4-wide 16-bit records of big scenes were tried in this loop too, with the deep part of the stack in local
             // memory to free L1 for the tree: L1 hits 7 -> 21 %, L2 sectors -25 %, but +14 % instructions in an ALU-bound
             // kernel: 462 ms against 420 ms for the general loop below — profiles/r02_tuning_sweeps.txt.)
-            constexpr uint32_t LEAFV = S4_LEAF;
+            constexpr uint32_t LEAFV = S4 ? S4_LEAF : Q16_LEAF;
             auto push = [&](uint32_t k) { sts32(sp_addr, k); sp_addr += STACK_STRIDE; };
             const bool had_ray = state == TRAVERSE;
             for (;;) {
@@ -474,6 +477,23 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                                 rr = lds128(na + 96u);
                             }
                             c = visit4(q0, q1, q2, q3, q4, q5, rr, inv_xy, noi_xy, inv.z, noi.z, closest.t, push);
+                        } else {
+                            uint4 qa, qb, qc, qd;
+                            const uint4* np = sv.nodes4_q + 4u * c;
+                            if (n_hot == 0u) ldg512u<0>(np, qa, qb, qc, qd);
+                            else if (c < n_hot) ldg512u<1>(np, qa, qb, qc, qd);
+                            else ldg512u<2>(np, qa, qb, qc, qd);
+                            float e;
+                            uint32_t k0 = box_cull_q16(qa.x, qa.y, qa.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
+                                              ? (((__float_as_uint(e) >> 20) << 21) | qa.w) : 0xffffffffu;
+                            uint32_t k1 = box_cull_q16(qb.x, qb.y, qb.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
+                                              ? (((__float_as_uint(e) >> 20) << 21) | qb.w) : 0xffffffffu;
+                            uint32_t k2 = box_cull_q16(qc.x, qc.y, qc.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
+                                              ? (((__float_as_uint(e) >> 20) << 21) | qc.w) : 0xffffffffu;
+                            uint32_t k3 = box_cull_q16(qd.x, qd.y, qd.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)
+                                              ? (((__float_as_uint(e) >> 20) << 21) | qd.w) : 0xffffffffu;
+                            k0 = sort4_park(k0, k1, k2, k3, push);
+                            c = k0 != 0xffffffffu ? (k0 & Q16_REF_MASK) : NONE;
                         }
                     }
 #if BVR_RECONVERGE
@@ -486,7 +506,11 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                             while (sp_addr != s_stack0) {
                                 sp_addr -= STACK_STRIDE;
                                 const uint32_t e = lds32(sp_addr);
-                                if (__uint_as_float(e & ~S4_REF_MASK) < closest.t) { c = e & S4_REF_MASK; break; }
+                                if constexpr (S4) {
+                                    if (__uint_as_float(e & ~S4_REF_MASK) < closest.t) { c = e & S4_REF_MASK; break; }
+                                } else {
+                                    if (__uint_as_float((e >> 21) << 20) < closest.t) { c = e & Q16_REF_MASK; break; }
+                                }
                             }
                         }
                     }
@@ -502,8 +526,13 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                     const uint32_t nblk = (uint32_t)__popc(blk);
                     if (nblk >= tune.leaf_batch_lanes || nblk == (uint32_t)__popc(trav)) {
                         if (parked) {
-                            const uint32_t m = pending & 0x3ffu;      // one sphere per leaf in these layouts
-                            test_sphere(sv, ray, a, m, lds128(s_spheres + m * 16u), closest);
+                            if constexpr (S4) {
+                                const uint32_t m = pending & 0x3ffu;      // one sphere per leaf in these layouts
+                                test_sphere(sv, ray, a, m, lds128(s_spheres + m * 16u), closest);
+                            } else {
+                                const uint32_t m = pending & 0xfffffu;
+                                test_sphere(sv, ray, a, m, __ldg(sv.spheres + m), closest);
+                            }
                             pending = NONE;
                         }
                     }
@@ -706,7 +735,8 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
     const size_t smem = (smem_scene ? scene_bytes : 0) + stack_bytes + (size_t)tune.n_top * 64u;
     if (smem > max_smem) return -1;
     auto kern = smem_scene ? megakernel_v3<THREADS, 0>
-                           : (w4 ? megakernel_v3<THREADS, 3> : (q16 ? megakernel_v3<THREADS, 2> : megakernel_v3<THREADS, 1>));
+                           : (w4 ? (tune.lean_w4 ? megakernel_v3<THREADS, 7> : megakernel_v3<THREADS, 3>)
+                                 : (q16 ? megakernel_v3<THREADS, 2> : megakernel_v3<THREADS, 1>));
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     int blocks_per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
@@ -730,10 +760,10 @@ int launch_selfcheck(const RenderParams& p, unsigned long long* counters, cudaSt
 
 int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32_t tree_depth,
                          unsigned int* pixel_counter, int threads, uint32_t shade_wait_lanes, uint32_t leaf_batch_lanes,
-                         bool no_both, uint32_t max_top, uint32_t n_hot, const uint32_t* tile_order, uint32_t* tile_cost,
-                         int sm_count, cudaStream_t stream) {
+                         bool no_both, uint32_t max_top, uint32_t n_hot, bool lean_w4, const uint32_t* tile_order,
+                         uint32_t* tile_cost, int sm_count, cudaStream_t stream) {
     if (p.cam.width > 0xffffu || p.shard.rows > 0xffffu) return -1;   // pixel packed as px | ly << 16
-    Tuning t{shade_wait_lanes, leaf_batch_lanes, max_top, n_hot, tile_order, tile_cost};
+    Tuning t{shade_wait_lanes, leaf_batch_lanes, max_top, n_hot, lean_w4 ? 1u : 0u, tile_order, tile_cost};
     switch (threads) {
         case 256: return launch_v3<256>(p, n_inner, n_models, tree_depth, pixel_counter, t, no_both, sm_count, stream);
         case 512: return launch_v3<512>(p, n_inner, n_models, tree_depth, pixel_counter, t, no_both, sm_count, stream);

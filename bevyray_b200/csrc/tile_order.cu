@@ -50,13 +50,16 @@ int launch_tile_order_update(uint32_t* tile_cost, uint32_t* tile_order, void* sc
     } else {
         if (first) { iota_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(iota, n_tiles, false); launches++; }
         size_t temp_bytes = cub_temp_bytes(n_tiles);
-        // stable sort: tiles of equal cost keep their row-major order, so the order is a pure function of the counters
+        // stable sort: tiles of equal cost keep their row-major order, so the order is a pure function of the counters.
+        // Only bits 4..19 of a counter take part (two 8-bit passes instead of four): 16 rays are noise, and a tile of more
+        // than 2^20 rays merely sorts as if it had fewer.
+        const int lo_bit = 4, hi_bit = 20;
         if (mode == 3)
             cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)tile_cost, keys_out, (const uint32_t*)iota,
-                                            tile_order, (int)n_tiles, 0, 32, stream);
+                                            tile_order, (int)n_tiles, lo_bit, hi_bit, stream);
         else
             cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, (const uint32_t*)tile_cost, keys_out,
-                                                      (const uint32_t*)iota, tile_order, (int)n_tiles, 0, 32, stream);
+                                                      (const uint32_t*)iota, tile_order, (int)n_tiles, lo_bit, hi_bit, stream);
         // (cub's kernels are library kernels: not counted among the launches the library reports as its own)
     }
     cudaMemsetAsync(tile_cost, 0, (size_t)n_tiles * sizeof(uint32_t), stream);
