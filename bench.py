@@ -299,6 +299,19 @@ def time_e2e(d, r, scene, step, host_rgba, steps, gpu_bvh=False, single_call=Non
     """The same frames through the public API with HOST buffers: scene upload (the reference re-uploads every frame,
     pipeline.rs:136-138) + render + read-back of the frame into pinned host memory, wall clock, max over ranks."""
     torch = d.torch
+
+    def one():
+        if gpu_bvh:
+            r.ctx.upload_scene_gpu_bvh(scene.models, scene.materials)
+        else:
+            r.upload_scene(scene.models, scene.materials, scene.nodes)
+        if single_call is not None:
+            single_call()
+        else:
+            step()
+            torch.cuda.synchronize()
+    for _ in range(2 if steps >= 3 else 1):   # untimed: the first host-buffer frame of a size allocates the library's pinned staging
+        one()
     rays = 0
     d.barrier()
     t0 = time.perf_counter()

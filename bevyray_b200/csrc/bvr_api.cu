@@ -54,7 +54,7 @@ struct PinnedBuffer {
 // only on request (bvr_reload_tuning); production uses the defaults.
 struct EnvTuning {
     int no_tight = 0, tight_pad = 100, no_q16 = 0, no_bvh4 = 0, gpu_validate = -1, wf_refill = 8;
-    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0, top_records = 0, hot_records = 512, w4_lean = 0, tile_order = -1, no_both = 0, gpu_lbvh = 0;
+    int mk_v1 = 0, mk_threads = 0, mk_wait = 0, mk_leaf = 0, selfcheck = 0, no_top = 0, top_records = 0, hot_records = 512, w4_lean = 1, tile_order = -1, no_both = 0, gpu_lbvh = 0;
 };
 
 struct BvrContext {
@@ -182,7 +182,7 @@ EnvTuning read_env_tuning() {
     t.selfcheck = env_int("BVR_SELFCHECK", 0);
     t.no_top = env_int("BVR_NO_TOP", 0);
     t.top_records = env_int("BVR_TOP_RECORDS", 0);
-    t.w4_lean = env_int("BVR_W4_LEAN", 0);
+    t.w4_lean = env_int("BVR_W4_LEAN", 1);   // 0: the general traversal loop on the 4-wide 16-bit records (MODE 3 instead of 7)
     t.hot_records = env_int("BVR_HOT_RECORDS", 512);   // 32 KB of records: what the stacks leave of L1 (profiles/r02_tuning_sweeps.txt)
     t.no_both = env_int("BVR_NO_BOTH", 0);
     // -1 (default): heaviest tile of the previous frame first when the frame is big enough to repay the sort;

@@ -449,9 +449,9 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             //   pending = a parked leaf (tested with the others' once a lane cannot go on without its test).
             // A lane with nothing in hand, nothing parked and an empty stack is idle: its ray is finished (or it has
             // none); idle lanes fall through every step without a state test.
-            // (The 4-wide 16-bit records of big scenes were tried in this loop too, with the deep part of the stack in local
-            // memory to free L1 for the tree: L1 hits 7 -> 21 %, L2 sectors -25 %, but +14 % instructions in an ALU-bound
-            // kernel: 462 ms against 420 ms for the general loop below — profiles/r02_tuning_sweeps.txt.)
+            // (Parking a popped leaf on the spot and popping on until the lane holds an inner record again — so that every
+            // step is a visit — was tried: C2 48.4 -> 53.3 ms, C4 371 -> 399 ms; the longer divergent loop costs more than
+            // the saved step.  So was a hybrid stack with its deep part in local memory: profiles/r02_tuning_sweeps.txt.)
             constexpr uint32_t LEAFV = S4 ? S4_LEAF : Q16_LEAF;
             auto push = [&](uint32_t k) { sts32(sp_addr, k); sp_addr += STACK_STRIDE; };
             const bool had_ray = state == TRAVERSE;

@@ -66,7 +66,7 @@ def test_small_scene_layouts(bvr, oracle, ctx, rtiow, knobs, env):
 @pytest.mark.parametrize("gpu_bvh", [False, True], ids=["host-ploc", "gpu-lbvh"])
 @pytest.mark.parametrize("env", [dict(), dict(BVR_NO_BVH4=1), dict(BVR_NO_Q16=1), dict(BVR_MK_THREADS=768), dict(BVR_NO_TOP=1),
                                  dict(BVR_TOP_RECORDS=1), dict(BVR_TOP_RECORDS=37), dict(BVR_TOP_RECORDS=100000), dict(BVR_HOT_RECORDS=300),
-                                 dict(BVR_TOP_RECORDS=21, BVR_HOT_RECORDS=85), dict(BVR_W4_LEAN=1), dict(BVR_W4_LEAN=1, BVR_MK_THREADS=768), dict(BVR_NO_BVH4=1, BVR_NO_TOP=1)],
+                                 dict(BVR_TOP_RECORDS=21, BVR_HOT_RECORDS=85), dict(BVR_W4_LEAN=0), dict(BVR_W4_LEAN=0, BVR_MK_THREADS=768), dict(BVR_W4_LEAN=0, BVR_HOT_RECORDS=0), dict(BVR_NO_BVH4=1, BVR_NO_TOP=1)],
                          ids=lambda e: "-".join(f"{k[4:]}={v}" for k, v in e.items()) or "default")
 def test_big_scene_layouts(bvr, oracle, ctx, knobs, env, gpu_bvh):
     """30k random spheres (C4's density): the records live in HBM/L2.  Also through the GPU-built tree, whose
