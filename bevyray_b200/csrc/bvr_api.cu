@@ -925,7 +925,7 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
             const int candidates[4] = {1024, 768, 512, 256};
             // pixel-queue order: heaviest tiles first, judged by the previous frame of the same size (tile_order.cu)
             const uint32_t n_tiles = ((p.cam.width + 7u) / 8u) * ((p.shard.rows + 3u) / 4u);
-            // (the sort costs ~40 us per frame: worth it from about 2^24 pixel samples, i.e. frames of a few milliseconds)
+            // (three small kernels per frame: worth it from about 2^24 pixel samples, i.e. frames of a few milliseconds)
             const int order_mode = ctx->tune.tile_order >= 0 ? ctx->tune.tile_order
                                    : ((uint64_t)n_tiles * 32u * p.cam.sample_count >= (1ull << 24) ? 2 : 0);
             const bool ordered = order_mode != 0 && n_tiles > 0;

@@ -131,7 +131,8 @@ int launch_megakernel_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_mod
 // ---- pixel-queue order (tile_order.cu) ----
 // The megakernel hands out 8x4 tiles through a queue.  A pixel is a sequential chain (one RNG stream, raytrace.wgsl:89),
 // so the frame ends when the slowest chain does: tiles are handed out heaviest first, judged by the rays each tile cost
-// in the PREVIOUS frame of the same size.  scratch: tile_order_scratch_bytes(n); cost: n u32 (zeroed by the update).
+// in the PREVIOUS frame of the same size (counting sort over logarithmic cost classes).  scratch:
+// tile_order_scratch_bytes(n); cost: n u32 (zeroed by the update).
 // mode: 2 = heaviest first, 3 = lightest first (experiment), 1 = reversed row-major (experiment)
 size_t tile_order_scratch_bytes(uint32_t n_tiles);
 int launch_tile_order_update(uint32_t* tile_cost, uint32_t* tile_order, void* scratch, uint32_t n_tiles, int mode, bool first,

@@ -5,10 +5,10 @@
 // A frame therefore ends with a tail in which most lanes have run out of pixels while a few finish heavy ones.  Handing
 // out the heaviest tiles FIRST (longest-processing-time-first list scheduling) keeps that tail short.  "Heaviest" is
 // judged by what each tile cost in the previous frame of the same size: the render kernel adds every pixel's ray count
-// to its tile's counter, and this file turns the counters into the next frame's order with one radix sort.  Ordering
-// cannot change an image — pixels are independent — only when each one is computed.
-
-#include <cub/device/device_radix_sort.cuh>
+// to its tile's counter, and the three small kernels below turn the counters into the next frame's order — a counting
+// sort over 1024 logarithmic cost classes (5 bits of exponent, 5 bits of mantissa: 3 % resolution at any magnitude).
+// Ordering cannot change an image — pixels are independent — only when each one is computed; inside one cost class the
+// order is whatever the atomics make it.
 
 #include "kernels.cuh"
 
@@ -16,54 +16,78 @@ namespace bvr {
 
 namespace {
 
+constexpr uint32_t N_CLASSES = 1024;
+
+__device__ __forceinline__ uint32_t cost_class(uint32_t cost) {
+    const uint32_t e = 31u - (uint32_t)__clz((int)(cost | 1u));        // position of the leading one, 0..31
+    const uint32_t m = e >= 5u ? (cost >> (e - 5u)) & 31u : (cost << (5u - e)) & 31u;
+    return (e << 5) | m;
+}
+
 __global__ void iota_kernel(uint32_t* __restrict__ v, uint32_t n, bool reversed) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = reversed ? n - 1u - i : i;
 }
 
-size_t align256(size_t x) { return (x + 255u) & ~(size_t)255u; }
+__global__ void class_count_kernel(const uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ classes) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&classes[cost_class(cost[i])], 1u);
+}
 
-size_t cub_temp_bytes(uint32_t n) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                              (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
-    return bytes;
+// classes[c] := number of tiles in the classes handed out BEFORE class c (heavier ones, or lighter ones when ascending)
+__global__ void __launch_bounds__(N_CLASSES) class_scan_kernel(uint32_t* __restrict__ classes, bool ascending) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t c = ascending ? t : N_CLASSES - 1u - t;             // thread t owns the t-th class in hand-out order
+    const uint32_t v = classes[c];
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31u) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= (uint32_t)o) w += y;
+        }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    classes[c] = (warp ? warp_sums[warp - 1] : 0u) + x - v;
+}
+
+__global__ void class_scatter_kernel(uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ classes,
+                                     uint32_t* __restrict__ order) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    order[atomicAdd(&classes[cost_class(cost[i])], 1u)] = i;
+    cost[i] = 0u;                                                       // the counters start the next frame at zero
 }
 
 }  // namespace
 
-// scratch = [iota n][sorted keys n][cub temp]
-size_t tile_order_scratch_bytes(uint32_t n_tiles) {
-    return 2u * align256((size_t)n_tiles * sizeof(uint32_t)) + align256(cub_temp_bytes(n_tiles));
-}
+size_t tile_order_scratch_bytes(uint32_t) { return N_CLASSES * sizeof(uint32_t); }
 
 int launch_tile_order_update(uint32_t* tile_cost, uint32_t* tile_order, void* scratch, uint32_t n_tiles, int mode, bool first,
                              cudaStream_t stream) {
     if (n_tiles == 0) return 0;
-    int launches = 0;
-    char* base = static_cast<char*>(scratch);
-    uint32_t* iota = reinterpret_cast<uint32_t*>(base);
-    uint32_t* keys_out = reinterpret_cast<uint32_t*>(base + align256((size_t)n_tiles * sizeof(uint32_t)));
-    void* temp = base + 2u * align256((size_t)n_tiles * sizeof(uint32_t));
-    if (mode == 1) {
-        if (first) { iota_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(tile_order, n_tiles, true); launches++; }
-    } else {
-        if (first) { iota_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(iota, n_tiles, false); launches++; }
-        size_t temp_bytes = cub_temp_bytes(n_tiles);
-        // stable sort: tiles of equal cost keep their row-major order, so the order is a pure function of the counters.
-        // Only bits 4..19 of a counter take part (two 8-bit passes instead of four): 16 rays are noise, and a tile of more
-        // than 2^20 rays merely sorts as if it had fewer.
-        const int lo_bit = 4, hi_bit = 20;
-        if (mode == 3)
-            cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)tile_cost, keys_out, (const uint32_t*)iota,
-                                            tile_order, (int)n_tiles, lo_bit, hi_bit, stream);
-        else
-            cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, (const uint32_t*)tile_cost, keys_out,
-                                                      (const uint32_t*)iota, tile_order, (int)n_tiles, lo_bit, hi_bit, stream);
-        // (cub's kernels are library kernels: not counted among the launches the library reports as its own)
+    const uint32_t blocks = (n_tiles + 255u) / 256u;
+    if (mode == 1) {   // experiment: reversed row-major
+        if (first) iota_kernel<<<blocks, 256, 0, stream>>>(tile_order, n_tiles, true);
+        cudaMemsetAsync(tile_cost, 0, (size_t)n_tiles * sizeof(uint32_t), stream);
+        return first ? 1 : 0;
     }
-    cudaMemsetAsync(tile_cost, 0, (size_t)n_tiles * sizeof(uint32_t), stream);
-    return launches;
+    uint32_t* classes = static_cast<uint32_t*>(scratch);
+    cudaMemsetAsync(classes, 0, N_CLASSES * sizeof(uint32_t), stream);
+    class_count_kernel<<<blocks, 256, 0, stream>>>(tile_cost, n_tiles, classes);
+    class_scan_kernel<<<1, N_CLASSES, 0, stream>>>(classes, mode == 3);   // 3 = experiment: lightest first
+    class_scatter_kernel<<<blocks, 256, 0, stream>>>(tile_cost, n_tiles, classes, tile_order);
+    return 3;
 }
 
 }  // namespace bvr
