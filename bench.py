@@ -76,9 +76,12 @@ def sharding_note(world, shard, wl, strip_rows):
     if world == 1:
         return "none"
     if shard == "samples":
-        per = [wl["spp"] // world + (1 if g < wl["spp"] % world else 0) for g in range(world)]
+        base, rem = divmod(wl["spp"], world)
+        per = (f"{base} per rank + one more on the 8x4 tiles of class (tx + ty + rank) % {world} < {rem} (every pixel gets {wl['spp']}, "
+               "every rank the same work)") if rem and base else str([base + (1 if g < rem else 0) for g in range(world)])
         return (f"samples: the frame's {wl['spp']} spp shared out as {per}, distinct seed per rank, partial frames weighted "
-                "by their share, NCCL reduce to rank 0")
+                "by their share inside the render kernel, which stores them straight into the rank's slot on rank 0 (peer memory "
+                "over NVLink); one small all-reduce, then rank 0 adds the slots in rank order")
     return f"tiles: {strip_rows}-row strips interleaved over ranks, NCCL all_gather + de-interleave kernel"
 
 
@@ -335,29 +338,32 @@ def time_e2e(d, r, scene, step, host_rgba, steps, gpu_bvh=False, single_call=Non
 
 
 def check_sample_parity(d, bvr, r, scene, wl, W, H, kernel, traversal, frame):
-    """Rank 0: the reduced frame must equal the share-weighted sum of the ranks' partial frames, each rendered here on
-    one GPU with that rank's seed and sample share.  NCCL's summation order is its own, so the comparison allows a few
-    ulps (2e-6 absolute on values in [0,1]); with two ranks it is exact."""
+    """Rank 0: the reduced frame must equal the sum of the ranks' weighted partial frames, each rendered here on one GPU
+    with that rank's seed, sample count, flags and weight (ShardedRenderer.last_plan) and added up in rank order.  The fused exchange over peer memory adds
+    the slots in that same order, so the two must agree BIT FOR BIT; only the NCCL fallback (no peer memory), whose
+    summation order is its own, gets a few ulps (2e-6 absolute on values in [0,1])."""
     from bevyray_b200.distributed import seed_for_rank, split_samples
     torch = d.torch
     if d.rank != 0:
         return None
     ctx = bvr.Context(d.local_rank)
     ctx.upload_scene(scene.models, scene.materials, scene.nodes)
-    acc = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
-    part = torch.empty_like(acc)
-    for g, share in enumerate(split_samples(wl["spp"], d.world)):
-        if share == 0:
+    acc = None
+    part = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    for g, (count, flags, weight) in enumerate(r.last_plan):       # what rank g rendered: sample count, flags, weight
+        if count == 0:
             continue
-        cam = make_cam(bvr, wl, share)
-        ctx.render_device(cam, 3, bvr.make_window(seed_for_rank(BASE_SEED, g, d.world, "samples"), H),
-                          bvr.make_options(W, kernel, traversal), rgba=part.data_ptr())
+        cam = make_cam(bvr, wl, count)
+        opts = bvr.make_options(W, kernel, traversal, output_weight=weight)
+        opts.flags |= flags
+        ctx.render_device(cam, 3, bvr.make_window(seed_for_rank(BASE_SEED, g, d.world, "samples"), H), opts, rgba=part.data_ptr())
         ctx.sync()
-        acc += part * np.float32(share / float(wl["spp"]))
+        acc = part.clone() if acc is None else acc + part
     torch.cuda.synchronize()
     diff = float((acc - frame).abs().max())
     ctx.close()
-    return "ok" if diff <= 2e-6 else f"FAILED: sample-sharded frame differs from the weighted per-seed frames by {diff:.3g}", diff
+    tol = 0.0 if r._slots else 2e-6
+    return "ok" if diff <= tol else f"FAILED: sample-sharded frame differs from the weighted per-seed frames by {diff:.3g}", diff
 
 
 def check_tile_parity(d, bvr, scene, wl, W, H, kernel, traversal, frame):
@@ -478,8 +484,8 @@ def run_leg(d, bvr, capi, key, args, peaks, steps, warmup, with_cpu, gpu_bvh=Fal
                                         else "FAILED")
             line["multi_gpu_parity_detail"] = parity
             line["limiter"] = ("samples: fixed per-frame cost that does not shrink with 1/N — kernel launch + scene staging into "
-                               "shared memory per CTA, the pixel-queue tail (the heaviest pixel is a chain of spp_g samples), one "
-                               f"{W * H * 16 / 1e6:.0f} MB scale kernel and one ncclReduce of the fp32 frame"
+                               "shared memory per CTA, the pixel-queue tail (the heaviest pixel is a chain of spp_g samples), one small "
+                               f"all-reduce and rank 0's sum over the {d.world} slots of {W * H * 16 / 1e6:.0f} MB"
                                if args.shard == "samples" else tiles and tiles["limiter"])
             if tiles:
                 line.setdefault("extra", {})["tiles"] = tiles

@@ -35,6 +35,13 @@ KERNEL_AUTO, KERNEL_MEGAKERNEL, KERNEL_WAVEFRONT, KERNEL_CTA_WAVEFRONT = 0, 1, 2
 TRAVERSAL_AUTO, TRAVERSAL_REFERENCE_ORDER = 0, 1
 ARRAY_MODELS, ARRAY_MATERIALS, ARRAY_BVH_NODES = 0, 1, 2
 RENDER_DEFER_COMPOSITE = 1
+RENDER_EXTRA_SAMPLE = 2
+
+
+def render_extra_sample_bits(modulus, phase, count):
+    """BVR_RENDER_EXTRA_SAMPLE_BITS of include/bevyray_b200.h"""
+    return RENDER_EXTRA_SAMPLE | (int(modulus) << 8) | (int(phase) << 16) | (int(count) << 24)
+
 
 
 class BvrModel(C.Structure):
@@ -73,7 +80,7 @@ class BvrDirtyRange(C.Structure):
 class BvrRenderOptions(C.Structure):
     _fields_ = [("width", C.c_uint32), ("kernel", C.c_uint32), ("traversal", C.c_uint32),
                 ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("strip_rows", C.c_uint32),
-                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32), ("output_weight", C.c_float)]
 
 
 class BvrOutputs(C.Structure):
@@ -94,6 +101,8 @@ class BvrhStandardMaterial(C.Structure):
 
 assert C.sizeof(BvrModel) == 32 and C.sizeof(BvrMaterial) == 32 and C.sizeof(BvrBvhNode) == 48
 assert C.sizeof(BvrCamera) == 80 and C.sizeof(BvrRaytraceLevel) == 32 and C.sizeof(BvrWindow) == 16
+
+PEER_HANDLE_BYTES = 64
 
 _P = C.POINTER
 _vp, _u32, _u64, _sz, _f, _i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_float, C.c_int
@@ -120,6 +129,11 @@ SIGNATURES = {
     "bvr_axpby_device": (_i, [_vp, _vp, _f, _vp, _f, _sz]),
     "bvr_composite_device": (_i, [_vp, _P(BvrCamera), _P(BvrRaytraceLevel), _vp, _vp, _vp, _vp, _sz]),
     "bvr_unshard_device": (_i, [_vp, _vp, _sz, _vp, _u32, _u32, _u32, _u32, _u32]),
+    "bvr_peer_alloc": (_i, [_vp, _sz, _P(_vp), _vp]),
+    "bvr_peer_open": (_i, [_vp, _vp, _P(_vp)]),
+    "bvr_peer_close": (_i, [_vp, _vp]),
+    "bvr_peer_free": (_i, [_vp, _vp]),
+    "bvr_sum_slots_device": (_i, [_vp, _vp, _sz, _u32, _u64, _vp, _sz]),
     "bvr_get_stats": (_i, [_vp, _P(BvrStats)]),
     "bvr_bench_fp32_peak": (_i, [_i, _P(_f)]),
     "bvr_bench_l2_bandwidth": (_i, [_i, _P(_f)]),

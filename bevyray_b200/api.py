@@ -48,10 +48,12 @@ def make_window(random_seed, height):
     return w
 
 
-def make_options(width, kernel=capi.KERNEL_AUTO, traversal=capi.TRAVERSAL_AUTO, shard_index=0, shard_count=0, strip_rows=0):
+def make_options(width, kernel=capi.KERNEL_AUTO, traversal=capi.TRAVERSAL_AUTO, shard_index=0, shard_count=0, strip_rows=0,
+                 output_weight=0.0):
     o = capi.BvrRenderOptions()
     o.width, o.kernel, o.traversal = int(width), int(kernel), int(traversal)
     o.shard_index, o.shard_count, o.strip_rows = int(shard_index), int(shard_count), int(strip_rows)
+    o.output_weight = float(output_weight)   # 0 = none
     return o
 
 
@@ -248,6 +250,29 @@ class Context:
         lv = level if isinstance(level, capi.BvrRaytraceLevel) else make_level(level)
         self._check(lib.bvr_composite_device(self._h, C.byref(camera), C.byref(lv), C.c_void_p(d_rgba), C.c_void_p(d_rt_depth),
                                              C.c_void_p(d_raster_rgba or None), C.c_void_p(d_raster_depth or None), n_pixels))
+
+    # ---- peer memory for the fused sample-sharding exchange (bevyray_b200.h) ----
+    def peer_alloc(self, nbytes):
+        """(device pointer, 64-byte handle another process can open)"""
+        ptr = C.c_void_p()
+        handle = (C.c_uint8 * capi.PEER_HANDLE_BYTES)()
+        self._check(lib.bvr_peer_alloc(self._h, nbytes, C.byref(ptr), C.cast(handle, C.c_void_p)))
+        return int(ptr.value), bytes(handle)
+
+    def peer_open(self, handle):
+        ptr = C.c_void_p()
+        buf = (C.c_uint8 * capi.PEER_HANDLE_BYTES).from_buffer_copy(handle)
+        self._check(lib.bvr_peer_open(self._h, C.cast(buf, C.c_void_p), C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr):
+        self._check(lib.bvr_peer_close(self._h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr):
+        self._check(lib.bvr_peer_free(self._h, C.c_void_p(ptr)))
+
+    def sum_slots_device(self, d_slots, slot_stride_floats, n_slots, mask, d_dst, n):
+        self._check(lib.bvr_sum_slots_device(self._h, C.c_void_p(d_slots), slot_stride_floats, n_slots, mask, C.c_void_p(d_dst), n))
 
     def unshard_device(self, d_gathered, shard_stride_words, d_full, width, height, channels, shard_count, strip_rows):
         self._check(lib.bvr_unshard_device(self._h, C.c_void_p(d_gathered), shard_stride_words, C.c_void_p(d_full),

@@ -7,6 +7,7 @@
 #include "../../include/bevyray_b200.h"
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -856,6 +857,19 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     p.reference_order = (opts->traversal == BVR_TRAVERSAL_REFERENCE_ORDER || (may_truncate && !ctx->tree_is_ours) ||
                          ctx->tree_depth + 1 > BVR_FAST_STACK) ? 1u : 0u;
     p.strict_slab = far_out <= BVR_FAST_MAX_EXTENT ? 0u : 1u;   // too far from the origin for the fast box arithmetic
+    p.out_weight = opts->output_weight == 0.0f ? 1.0f : opts->output_weight;
+    p.weight_in_kernel = 0u;
+    p.extra_modulus = p.extra_phase = p.extra_count = 0u;
+    if (opts->flags & BVR_RENDER_EXTRA_SAMPLE) {
+        p.extra_modulus = (opts->flags >> 8) & 0xffu;
+        p.extra_phase = (opts->flags >> 16) & 0xffu;
+        p.extra_count = (opts->flags >> 24) & 0xffu;
+        if (p.extra_modulus == 0u || p.extra_count > p.extra_modulus || camera->sample_count == 0u)
+            return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "BVR_RENDER_EXTRA_SAMPLE: modulus 1..255, count <= modulus, sample_count >= 1");
+        if (opts->kernel == BVR_KERNEL_WAVEFRONT || opts->kernel == BVR_KERNEL_CTA_WAVEFRONT || p.reference_order || p.strict_slab ||
+            ctx->tune.mk_v1 || p.cam.level == 0u)
+            return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "BVR_RENDER_EXTRA_SAMPLE needs the persistent megakernel (near-first traversal)");
+    }
     *out = p;
     return BVR_OK;
 }
@@ -958,6 +972,8 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
                 if (forced) break;
             }
             if (n < 0) cudaGetLastError();
+            else p.weight_in_kernel = 1u;   // megakernel_v3 applies output_weight as it stores
+            if (n < 0 && p.extra_modulus) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "BVR_RENDER_EXTRA_SAMPLE: the megakernel does not fit this scene");
             if (n >= 0 && ordered) {
                 launches += launch_tile_order_update(tile_cost, ctx->tile_order.as<uint32_t>(), ctx->tile_scratch.ptr, n_tiles,
                                                      order_mode, tile_first, ctx->stream);
@@ -967,6 +983,12 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
         if (n < 0) n = launch_megakernel(p, ctx->stream);   // reference-order traversal, or scene too deep
         launches += n;
         launches += launch_selfcheck(p, ctx->ray_counter.as<unsigned long long>() + 1, ctx->stream);
+    }
+    if (p.out_weight != 1.0f && !p.weight_in_kernel) {
+        // the other kernels (level Skip's copy, one thread per pixel, the wavefront pipelines) get the weight as a pass of its own
+        const size_t px = (size_t)p.cam.width * p.shard.rows;
+        if (p.out_rgba) launches += launch_scale(reinterpret_cast<float*>(p.out_rgba), p.out_weight, px * 4u, ctx->stream);
+        if (p.out_rt_depth) launches += launch_scale(p.out_rt_depth, p.out_weight, px, ctx->stream);
     }
     BVR_CK(cudaGetLastError());
     BVR_CK(cudaEventRecord(ctx->ev_render1, ctx->stream));
@@ -978,6 +1000,15 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
     uint64_t rows = 0;
     for (uint32_t ly = 0; ly < p.shard.rows; ly++) if (shard_global_row(p.shard, ly) < p.cam.height) rows++;
     ctx->stats.paths = p.cam.level == 0u ? 0u : rows * (uint64_t)p.cam.width * p.cam.sample_count;
+    if (p.extra_modulus) {   // + one path per pixel of the tiles that take an extra sample
+        for (uint32_t ly = 0; ly < p.shard.rows; ly++) {
+            const uint32_t gy = shard_global_row(p.shard, ly);
+            if (gy >= p.cam.height) continue;
+            for (uint32_t tx = 0; tx * 8u < p.cam.width; tx++)
+                if ((tx + (gy >> 2) + p.extra_phase) % p.extra_modulus < p.extra_count)
+                    ctx->stats.paths += std::min(8u, p.cam.width - tx * 8u);
+        }
+    }
     return BVR_OK;
 }
 
@@ -1111,6 +1142,64 @@ int bvr_composite_device(BvrContext* ctx, const BvrCamera* camera, const BvrRayt
     ctx->stats.kernel_launches += (uint64_t)launch_composite(reinterpret_cast<float4*>(d_rgba), d_rt_depth,
                                                              reinterpret_cast<const float4*>(d_raster_rgba), d_raster_depth,
                                                              c, n_pixels, ctx->stream);
+    BVR_CK(cudaGetLastError());
+    return BVR_OK;
+}
+
+int bvr_peer_alloc(BvrContext* ctx, size_t bytes, void** d_ptr, uint8_t* handle_out) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    if (!d_ptr || !handle_out || bytes == 0) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "bad peer allocation arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == BVR_PEER_HANDLE_BYTES, "peer handle size");
+    cudaSetDevice(ctx->device);
+    void* ptr = nullptr;
+    BVR_CK(cudaMalloc(&ptr, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) { cudaFree(ptr); return fail_cuda(ctx, e, "cudaIpcGetMemHandle"); }
+    std::memcpy(handle_out, &h, sizeof h);
+    *d_ptr = ptr;
+    return BVR_OK;
+}
+
+int bvr_peer_open(BvrContext* ctx, const uint8_t* handle, void** d_ptr) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    if (!d_ptr || !handle) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "bad peer handle arguments");
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void* ptr = nullptr;
+    BVR_CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = ptr;
+    return BVR_OK;
+}
+
+int bvr_peer_close(BvrContext* ctx, void* d_ptr) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    cudaSetDevice(ctx->device);
+    if (d_ptr) { BVR_CK(cudaStreamSynchronize(ctx->stream)); BVR_CK(cudaIpcCloseMemHandle(d_ptr)); }
+    return BVR_OK;
+}
+
+int bvr_peer_free(BvrContext* ctx, void* d_ptr) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    cudaSetDevice(ctx->device);
+    if (d_ptr) { BVR_CK(cudaStreamSynchronize(ctx->stream)); BVR_CK(cudaFree(d_ptr)); }
+    return BVR_OK;
+}
+
+int bvr_sum_slots_device(BvrContext* ctx, const float* d_slots, size_t slot_stride_floats, uint32_t n_slots, uint64_t mask,
+                         float* d_dst, size_t n) {
+    if (!ctx) return BVR_ERR_INVALID_ARGUMENT;
+    ctx->error.clear();
+    if (n && (!d_slots || !d_dst)) return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "null device pointer");
+    if (n_slots == 0 || n_slots > 64u || (n & 3u) || (slot_stride_floats & 3u) || slot_stride_floats < n)
+        return fail(ctx, BVR_ERR_INVALID_ARGUMENT, "bad slot geometry (1..64 slots, float4-aligned sizes)");
+    cudaSetDevice(ctx->device);
+    ctx->stats.kernel_launches += (uint64_t)launch_sum_slots(d_slots, slot_stride_floats, n_slots, mask, d_dst, n, ctx->stream);
     BVR_CK(cudaGetLastError());
     return BVR_OK;
 }

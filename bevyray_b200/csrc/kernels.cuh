@@ -33,6 +33,10 @@ struct RenderParams {
     float4* selfcheck_log;             // BVR_SELFCHECK: 2 x float4 per logged ray (o.xyz, t) (d.xyz, model bits), or null
     unsigned int* selfcheck_count;     // rays logged so far (may exceed the capacity: the excess is dropped)
     uint32_t selfcheck_cap;
+    float out_weight;                  // BvrRenderOptions.output_weight (1 = none): applied to rgba and rt_depth as they are stored
+    uint32_t extra_modulus, extra_phase, extra_count;   // BVR_RENDER_EXTRA_SAMPLE (modulus 0 = off): the pixels of the 8x4 tiles
+                                       // with ((tx + ty + phase) % modulus) < count take one sample more (megakernel_v3 only)
+    uint32_t weight_in_kernel;         // set by the kernel that applies out_weight itself (others get a scale pass afterwards)
 };
 
 // Wavefront path state in HBM (SoA, indexed by shard-local pixel slot) and the work queues.
@@ -151,6 +155,9 @@ int launch_wavefront(WavefrontParams w, uint32_t n_inner, uint32_t n_models, uin
 int launch_copy_raster(const RenderParams& p, cudaStream_t stream);   // level 0: raytrace.wgsl:97-99
 
 // ---- multi-GPU helpers (shard_kernels.cu) ----
+int launch_scale(float* dst, float w, size_t n, cudaStream_t stream);
+int launch_sum_slots(const float* slots, size_t slot_stride, uint32_t n_slots, unsigned long long mask, float* dst, size_t n,
+                     cudaStream_t stream);
 int launch_axpby(float* dst, float dst_weight, const float* src, float src_weight, size_t n, cudaStream_t stream);
 int launch_composite(float4* rgba, const float* rt_depth, const float4* raster_rgba, const float* raster_depth,
                      const CameraParams& cam, size_t n, cudaStream_t stream);

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 }
                 if (bounce == 0u) {
                     first_depth = closest.t;
-                    if (sidx == 0u && (p.out_primary_id || p.out_primary_depth)) {   // first sample's primary hit
+                    if ((sidx << 1) == 0u && (p.out_primary_id || p.out_primary_depth)) {   // first sample's primary hit
                         const size_t lpix = (size_t)(pxy >> 16) * cam.width + (pxy & 0xffffu);
                         if (p.out_primary_id) p.out_primary_id[lpix] = closest.t == BVR_INF ? 0xffffffffu : closest.model;
                         if (p.out_primary_depth) p.out_primary_depth[lpix] = closest.t;
@@ -336,10 +336,11 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             }
         }
         // --- A4: pixel store (average, fused composite raytrace.wgsl:104-120) ---
-        if (state == NEW_PATH && sidx >= cam.sample_count) {
+        // (bit 31 of sidx = this pixel takes one sample more than cam.sample_count: BVR_RENDER_EXTRA_SAMPLE, set in A5)
+        if (state == NEW_PATH && (sidx & 0x7fffffffu) >= cam.sample_count + (sidx >> 31)) {
             const uint32_t px = pxy & 0xffffu, ly = pxy >> 16;
             const uint32_t gy = shard_global_row(p.shard, ly);
-            const float n = (float)cam.sample_count;
+            const float n = (float)(cam.sample_count + (sidx >> 31));
             float4 out = make_float4(fdiv(total.x, n), fdiv(total.y, n), fdiv(total.z, n), 1.0f);
             const float depth_avg = fdiv(total_depth, n);
             if (cam.level == 1u || cam.level == 2u) {
@@ -347,8 +348,11 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 if (raster_wins(cam, p.raster_depth[gpix], depth_avg)) out = p.raster_rgba[gpix];
             }
             const size_t lpix = (size_t)ly * cam.width + px;
-            if (p.out_rgba) p.out_rgba[lpix] = out;
-            if (p.out_rt_depth) p.out_rt_depth[lpix] = depth_avg;
+            // sample sharding: the partial frame leaves the kernel weighted by this rank's share of the samples, and
+            // out_rgba may be this rank's slot in a buffer on ANOTHER GPU (the stores travel over NVLink as pixels finish)
+            const float ow = p.extra_modulus ? fmul(n, p.out_weight) : p.out_weight;   // uneven samples: the weight of ONE sample x n
+            if (p.out_rgba) p.out_rgba[lpix] = ow == 1.0f ? out : make_float4(fmul(out.x, ow), fmul(out.y, ow), fmul(out.z, ow), fmul(out.w, ow));
+            if (p.out_rt_depth) p.out_rt_depth[lpix] = ow == 1.0f ? depth_avg : fmul(depth_avg, ow);
             if (cam.sample_count == 0u) {
                 if (p.out_primary_id) p.out_primary_id[lpix] = 0xffffffffu;
                 if (p.out_primary_depth) p.out_primary_depth[lpix] = BVR_INF;
@@ -384,6 +388,8 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                         v = pixel_v(cam, gy);
                         rng = pixel_seed(cam, u, v);
                         sidx = 0u;
+                        if (p.extra_modulus && ((px >> 3) + (gy >> 2) + p.extra_phase) % p.extra_modulus < p.extra_count)
+                            sidx = 0x80000000u;
                         total = v3(0.0f, 0.0f, 0.0f);
                         total_depth = 0.0f;
                         state = NEW_PATH;
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         }
         if (__all_sync(full, state == DONE)) break;
         // --- A6: camera rays (raytrace.wgsl:139-156), one site ---
-        if (state == NEW_PATH && sidx < cam.sample_count) {
+        if (state == NEW_PATH && (sidx & 0x7fffffffu) < cam.sample_count + (sidx >> 31)) {
             ray = random_ray_from_uv(cam, u, v, rng);
             throughput = v3(1.0f, 1.0f, 1.0f);
             bounce = 0u;

@@ -19,6 +19,25 @@ __global__ void scale_kernel(float* __restrict__ dst, float w, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __fmul_rn(dst[i], w);
 }
 
+// Sample sharding over peer memory: dst = ((slot_0 + slot_1) + slot_2) + ... in slot order, over the slots named in `mask`
+// (a rank that got no samples leaves its slot untouched).  The first term is copied, not added to zero, and the order is
+// fixed, so the sum is a pure function of the slots.
+__global__ void sum_slots_kernel(const float4* __restrict__ slots, size_t slot_stride4, uint32_t n_slots, unsigned long long mask,
+                                 float4* __restrict__ dst, size_t n4) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool first = true;
+        for (uint32_t s = 0; s < n_slots; s++) {
+            if (!((mask >> s) & 1ull)) continue;
+            const float4 v = slots[s * slot_stride4 + i];
+            if (first) { acc = v; first = false; }
+            else acc = make_float4(__fadd_rn(acc.x, v.x), __fadd_rn(acc.y, v.y), __fadd_rn(acc.z, v.z), __fadd_rn(acc.w, v.w));
+        }
+        dst[i] = acc;
+    }
+}
+
 // fragment's depth composite (raytrace.wgsl:104-120) as a pass of its own: used when the ray-traced colour and depth
 // of one frame are the sum of several ranks' partial frames and can only be compared with the raster depth afterwards
 __global__ void composite_kernel(float4* __restrict__ rgba, const float* __restrict__ rt_depth,
@@ -47,6 +66,20 @@ __global__ void unshard_kernel(const uint32_t* __restrict__ gathered, size_t sha
 }
 
 }  // namespace
+
+int launch_scale(float* dst, float w, size_t n, cudaStream_t stream) {
+    if (n == 0) return 0;
+    scale_kernel<<<592, 256, 0, stream>>>(dst, w, n);
+    return 1;
+}
+
+int launch_sum_slots(const float* slots, size_t slot_stride, uint32_t n_slots, unsigned long long mask, float* dst, size_t n,
+                     cudaStream_t stream) {
+    if (n == 0) return 0;
+    sum_slots_kernel<<<1184, 256, 0, stream>>>(reinterpret_cast<const float4*>(slots), slot_stride / 4u, n_slots, mask,
+                                               reinterpret_cast<float4*>(dst), n / 4u);
+    return 1;
+}
 
 int launch_axpby(float* dst, float dw, const float* src, float sw, size_t n, cudaStream_t stream) {
     if (n == 0) return 0;

@@ -164,15 +164,27 @@ typedef struct BvrRenderOptions {
     uint32_t shard_count;
     uint32_t strip_rows;   /* 0 = default (8) */
     uint32_t flags;        /* BvrRenderFlags */
-    uint32_t reserved;
+    float    output_weight; /* 0 (or 1) = none.  Otherwise every rgba texel (all four channels) and every rt_depth texel is
+                              multiplied by it as it is stored: a rank's partial frame of a sample-sharded render leaves
+                              the kernel already weighted by its share of the samples */
 } BvrRenderOptions;
 
 typedef enum BvrRenderFlags {
     /* Levels 1-2: skip the depth composite (raytrace.wgsl:104-120) but keep the level's fallback depth for misses
      * (raytrace.wgsl:177-182).  For sample sharding: the partial frames of all ranks are summed first (colour AND
      * rt_depth), then bvr_composite_device compares the summed depth with the raster depth once. */
-    BVR_RENDER_DEFER_COMPOSITE = 1u
+    BVR_RENDER_DEFER_COMPOSITE = 1u,
+    /* Uneven sample counts, for sharing S samples out over N ranks when N does not divide S: the pixels of the 8x4 tiles
+     * (tx, ty) with ((tx + ty + PHASE) % MODULUS) < COUNT take ONE sample more than camera.sample_count, with
+     * MODULUS = flags bits 8-15 (1..255), PHASE = bits 16-23, COUNT = bits 24-31.  Rank g of N renders S / N samples with
+     * MODULUS = N, PHASE = g, COUNT = S % N: every pixel then gets exactly S samples over the ranks, and every rank the same
+     * amount of work.  With this flag output_weight is the weight of ONE sample (1 / S): a pixel with n samples is stored
+     * multiplied by n x output_weight.  Megakernel only (BVR_ERR_INVALID_ARGUMENT with the other kernels / traversals);
+     * camera.sample_count must be at least 1. */
+    BVR_RENDER_EXTRA_SAMPLE = 2u
 } BvrRenderFlags;
+#define BVR_RENDER_EXTRA_SAMPLE_BITS(modulus, phase, count) \
+    (BVR_RENDER_EXTRA_SAMPLE | ((uint32_t)(modulus) << 8) | ((uint32_t)(phase) << 16) | ((uint32_t)(count) << 24))
 
 /* Output planes.  Any pointer may be NULL (plane not produced / not copied).
  * For a sharded render each plane holds only this shard's rows, strips concatenated in order:
@@ -317,6 +329,24 @@ int bvr_composite_device(BvrContext* ctx, const BvrCamera* camera, const BvrRayt
 int bvr_unshard_device(BvrContext* ctx, const void* d_gathered, size_t shard_stride_words,
                        void* d_full, uint32_t width, uint32_t height, uint32_t channels,
                        uint32_t shard_count, uint32_t strip_rows);
+
+/* Sample sharding over peer memory (one process per GPU of ONE node).  Instead of scaling its partial frame and
+ * handing it to an NCCL reduce, every rank renders straight INTO its own slot of a buffer that lives on rank 0 — the
+ * render kernel's pixel stores go over NVLink as the pixels finish (output_weight above applies the share) — and rank 0
+ * adds the slots up in rank order once all ranks are done.  The exchange overlaps the rendering, the sum has a fixed
+ * order (bit-reproducible, unlike a reduction tree), and what is left on the critical path is one small barrier + one pass
+ * over the slots.
+ *   bvr_peer_alloc   cudaMalloc on this context's device + the 64-byte handle another process opens
+ *   bvr_peer_open    maps a buffer another rank allocated (peer access is enabled on first use)
+ *   bvr_peer_close / bvr_peer_free
+ *   bvr_sum_slots_device   d_dst[i] = ((slot_0[i] + slot_1[i]) + slot_2[i]) + ... over the slots whose bit is set in `mask` */
+#define BVR_PEER_HANDLE_BYTES 64
+int bvr_peer_alloc(BvrContext* ctx, size_t bytes, void** d_ptr, uint8_t* handle_out);
+int bvr_peer_open(BvrContext* ctx, const uint8_t* handle, void** d_ptr);
+int bvr_peer_close(BvrContext* ctx, void* d_ptr);
+int bvr_peer_free(BvrContext* ctx, void* d_ptr);
+int bvr_sum_slots_device(BvrContext* ctx, const float* d_slots, size_t slot_stride_floats, uint32_t n_slots, uint64_t mask,
+                         float* d_dst, size_t n);
 
 int bvr_get_stats(BvrContext* ctx, BvrStats* out);
 

@@ -62,7 +62,8 @@ pub struct BvrRenderOptions {
     pub shard_count: u32,
     pub strip_rows: u32,
     pub flags: u32,
-    pub reserved: u32,
+    /// 0 (or 1) = none; otherwise every rgba / rt_depth texel is multiplied by it as it is stored
+    pub output_weight: f32,
 }
 
 #[repr(C)]

@@ -17,6 +17,85 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
+@pytest.mark.parametrize("kernel,traversal", KERNELS, ids=KERNEL_IDS)
+def test_output_weight_is_one_rounding_per_texel(bvr, ctx, rtiow, kernel, traversal):
+    """BvrRenderOptions.output_weight (a rank's share in a sample-sharded frame): rgba and rt_depth leave the library
+    multiplied by it — inside the store of the production kernel, as a pass of its own after the others — and the
+    result is the unweighted plane times the weight, one IEEE multiplication per word; the other planes are untouched."""
+    W, H = 200, 113
+    cam = bvr.make_camera(position=(13, 2, 3), target=(0, 0, 0), fov=float(np.deg2rad(20)), aspect=W / H, sample_count=3, bounces=6)
+    win = bvr.make_window(0.37, H)
+    ctx.upload_scene(rtiow.models, rtiow.materials, rtiow.nodes)
+    plain = ctx.render(cam, 3, win, bvr.make_options(W, kernel, traversal))
+    wgt = np.float32(3.0 / 13.0)
+    got = ctx.render(cam, 3, win, bvr.make_options(W, kernel, traversal, output_weight=float(wgt)))
+    assert np.array_equal(bits(got["rgba"]), bits(plain["rgba"] * wgt))
+    assert np.array_equal(bits(got["rt_depth"]), bits(plain["rt_depth"] * wgt))
+    assert np.array_equal(got["primary_id"], plain["primary_id"])
+    assert np.array_equal(bits(got["primary_depth"]), bits(plain["primary_depth"]))
+    one = ctx.render(cam, 3, win, bvr.make_options(W, kernel, traversal, output_weight=1.0))
+    assert np.array_equal(bits(one["rgba"]), bits(plain["rgba"]))
+
+
+def test_extra_sample_tiles(bvr, ctx, rtiow):
+    """BVR_RENDER_EXTRA_SAMPLE: the pixels of the tiles of class (tx + ty + phase) % modulus < count take one sample more.
+    A pixel is its own RNG stream, so such a frame is the n-sample frame on those tiles and the (n-1)-sample frame on the
+    others, each weighted by its own sample count x output_weight; all four planes, and the ray count adds up."""
+    W, H, n, S = 203, 117, 3, 31
+    cam = lambda k: bvr.make_camera(position=(13, 2, 3), target=(0, 0, 0), fov=float(np.deg2rad(20)), aspect=W / H, sample_count=k, bounces=6)
+    win = bvr.make_window(0.37, H)
+    ctx.upload_scene(rtiow.models, rtiow.materials, rtiow.nodes)
+    lo = ctx.render(cam(n), 3, win, bvr.make_options(W))
+    rays_lo = ctx.stats()["rays"]
+    hi = ctx.render(cam(n + 1), 3, win, bvr.make_options(W))
+    ty, tx = np.mgrid[0:H, 0:W]
+    ty, tx = ty // 4, tx // 8
+    for modulus, phase, count in ((2, 0, 1), (2, 1, 1), (8, 3, 4), (5, 2, 0), (3, 1, 3)):
+        o = bvr.make_options(W, output_weight=1.0 / S)
+        o.flags |= bvr.capi.render_extra_sample_bits(modulus, phase, count)
+        got = ctx.render(cam(n), 3, win, o)
+        st = ctx.stats()
+        extra = ((tx + ty + phase) % modulus) < count
+        w_lo, w_hi = np.float32(n) * np.float32(1.0 / S), np.float32(n + 1) * np.float32(1.0 / S)
+        want_rgba = np.where(extra[..., None], hi["rgba"] * w_hi, lo["rgba"] * w_lo)
+        want_depth = np.where(extra, hi["rt_depth"] * w_hi, lo["rt_depth"] * w_lo)
+        assert np.array_equal(bits(got["rgba"]), bits(want_rgba)), (modulus, phase, count)
+        assert np.array_equal(bits(got["rt_depth"]), bits(want_depth))
+        assert np.array_equal(got["primary_id"], lo["primary_id"])
+        assert st["paths"] == W * H * n + int(extra.sum())
+        assert rays_lo <= st["rays"]
+    for kernel, traversal in ((2, 0), (3, 0), (1, 1)):      # only the megakernel's near-first walk takes uneven samples
+        o = bvr.make_options(W, kernel, traversal)
+        o.flags |= bvr.capi.render_extra_sample_bits(2, 0, 1)
+        with pytest.raises(RuntimeError):
+            ctx.render(cam(n), 3, win, o)
+    o = bvr.make_options(W)
+    o.flags |= bvr.capi.render_extra_sample_bits(2, 0, 1)
+    with pytest.raises(RuntimeError):
+        ctx.render(cam(0), 3, win, o)
+
+
+def test_sum_slots_adds_in_slot_order(bvr, ctx):
+    """bvr_sum_slots_device: dst = ((s0 + s1) + s2) + ... over the slots in the mask, first term copied."""
+    import torch
+    n, world = 4 * 1000, 5
+    g = torch.Generator(device="cuda").manual_seed(3)
+    slots = (torch.rand((world, n + 8), device="cuda", generator=g) * 3.0 - 1.0).contiguous()
+    dst = torch.full((n,), 7.0, device="cuda")
+    for mask in (0b11111, 0b10110, 0b00001, 0):
+        ctx.sum_slots_device(slots.data_ptr(), n + 8, world, mask, dst.data_ptr(), n)
+        ctx.sync()
+        want = torch.zeros(n, device="cuda")
+        first = True
+        for s in range(world):
+            if (mask >> s) & 1:
+                want = slots[s, :n].clone() if first else want + slots[s, :n]
+                first = False
+        assert torch.equal(dst, want), mask
+    with pytest.raises(RuntimeError):
+        ctx.sum_slots_device(slots.data_ptr(), n + 8, 65, 1, dst.data_ptr(), n)
+
+
 def check(got, want, keys=("primary_id", "primary_depth", "rt_depth", "rgba")):
     for k in keys:
         nbad = int((bits(got[k]) != bits(want[k])).sum())
