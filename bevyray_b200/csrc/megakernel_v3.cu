@@ -110,6 +110,11 @@ __global__ void selfcheck_kernel(const SceneView sv, const float4* __restrict__ 
     if (bad) atomicAdd(&counters[1], bad);
 }
 
+// BVR_RENDER_EXTRA_SAMPLE: does the pixel (px, global row gy) take one sample more than cam.sample_count?
+__device__ __forceinline__ bool extra_sample(const RenderParams& p, uint32_t px, uint32_t gy) {
+    return p.extra_modulus != 0u && ((px >> 3) + (gy >> 2) + p.extra_phase) % p.extra_modulus < p.extra_count;
+}
+
 struct Tuning {
     uint32_t shade_wait_lanes;   // leave phase B when this many lanes wait for shading
     uint32_t leaf_batch_lanes;   // test parked leaves when this many lanes hold one
@@ -205,7 +210,8 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
     int state = NEED_PIXEL;
     uint32_t pxy = 0;   // px | ly << 16
     float u = 0.0f, v = 0.0f;
-    uint32_t rng = 0, sidx = 0, bounce = 0;
+    uint32_t rng = 0, bounce = 0;
+    uint32_t sleft = 0;   // samples this pixel still has to take; bit 31 = its first sample has not been shaded yet
     V3 total = v3(0.0f, 0.0f, 0.0f);
     float total_depth = 0.0f, first_depth = BVR_INF;
     V3 throughput = v3(1.0f, 1.0f, 1.0f);
@@ -235,7 +241,8 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 }
                 if (bounce == 0u) {
                     first_depth = closest.t;
-                    if ((sidx << 1) == 0u && (p.out_primary_id || p.out_primary_depth)) {   // first sample's primary hit
+                    if ((int)sleft < 0) {   // first sample's primary hit
+                        sleft &= 0x7fffffffu;
                         const size_t lpix = (size_t)(pxy >> 16) * cam.width + (pxy & 0xffffu);
                         if (p.out_primary_id) p.out_primary_id[lpix] = closest.t == BVR_INF ? 0xffffffffu : closest.model;
                         if (p.out_primary_depth) p.out_primary_depth[lpix] = closest.t;
@@ -328,7 +335,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                     if (first_depth == BVR_INF) first_depth = cam.fallback_far;
                     total = vadd(total, sample_color);
                     total_depth = fadd(total_depth, first_depth);
-                    sidx++;
+                    sleft--;
                     state = NEW_PATH;
                 } else {
                     state = RAY_READY;
@@ -336,11 +343,11 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             }
         }
         // --- A4: pixel store (average, fused composite raytrace.wgsl:104-120) ---
-        // (bit 31 of sidx = this pixel takes one sample more than cam.sample_count: BVR_RENDER_EXTRA_SAMPLE, set in A5)
-        if (state == NEW_PATH && (sidx & 0x7fffffffu) >= cam.sample_count + (sidx >> 31)) {
+        if (state == NEW_PATH && sleft == 0u) {
             const uint32_t px = pxy & 0xffffu, ly = pxy >> 16;
             const uint32_t gy = shard_global_row(p.shard, ly);
-            const float n = (float)(cam.sample_count + (sidx >> 31));
+            // BVR_RENDER_EXTRA_SAMPLE: the pixels of some tiles took one sample more than cam.sample_count
+            const float n = (float)(cam.sample_count + (extra_sample(p, px, gy) ? 1u : 0u));
             float4 out = make_float4(fdiv(total.x, n), fdiv(total.y, n), fdiv(total.z, n), 1.0f);
             const float depth_avg = fdiv(total_depth, n);
             if (cam.level == 1u || cam.level == 2u) {
@@ -387,9 +394,8 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                         u = pixel_u(cam, px);
                         v = pixel_v(cam, gy);
                         rng = pixel_seed(cam, u, v);
-                        sidx = 0u;
-                        if (p.extra_modulus && ((px >> 3) + (gy >> 2) + p.extra_phase) % p.extra_modulus < p.extra_count)
-                            sidx = 0x80000000u;
+                        sleft = cam.sample_count + (extra_sample(p, px, gy) ? 1u : 0u);
+                        if (sleft) sleft |= 0x80000000u;
                         total = v3(0.0f, 0.0f, 0.0f);
                         total_depth = 0.0f;
                         state = NEW_PATH;
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
         }
         if (__all_sync(full, state == DONE)) break;
         // --- A6: camera rays (raytrace.wgsl:139-156), one site ---
-        if (state == NEW_PATH && (sidx & 0x7fffffffu) < cam.sample_count + (sidx >> 31)) {
+        if (state == NEW_PATH && sleft != 0u) {
             ray = random_ray_from_uv(cam, u, v, rng);
             throughput = v3(1.0f, 1.0f, 1.0f);
             bounce = 0u;
