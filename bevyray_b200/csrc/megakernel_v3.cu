@@ -42,6 +42,9 @@ enum Kind : int { K_NONE = 0, K_MISS = 1, K_METAL = 2, K_GLASS = 3, K_DIFFUSE = 
 #ifndef BVR_STEPS_PER_VOTE
 #define BVR_STEPS_PER_VOTE 2   // traversal steps between two rounds of warp votes
 #endif
+#ifndef BVR_W4_STEPS_PER_VOTE
+#define BVR_W4_STEPS_PER_VOTE 4   // ... on the records walked in HBM/L2 (C4: 1 / 2 / 3 / 4 steps = 384 / 369 / 367 / 363 ms)
+#endif
 
 // Culling-only slab test on (centre, half extent) boxes.  Per axis: tc = fma(c, 1/d, -o/d), th = h * |1/d|,
 // lo = tc - th, hi = tc + th — four FMA-pipe instructions instead of two FFMA + two FMNMX: the traversal loop is
@@ -467,9 +470,10 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             constexpr uint32_t LEAFV = S4 ? S4_LEAF : Q16_LEAF;
             auto push = [&](uint32_t k) { sts32(sp_addr, k); sp_addr += STACK_STRIDE; };
             const bool had_ray = state == TRAVERSE;
+            constexpr int STEPS = S4 ? BVR_STEPS_PER_VOTE : BVR_W4_STEPS_PER_VOTE;
             for (;;) {
 #pragma unroll
-                for (int rep = 0; rep < BVR_STEPS_PER_VOTE; rep++) {
+                for (int rep = 0; rep < STEPS; rep++) {
                     uint32_t c = cur;
                     if (c < LEAFV) {
                         if constexpr (S4) {
