@@ -540,8 +540,12 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                 const bool parked = pending != NONE;
                 const unsigned trav = __ballot_sync(full, cur != NONE || parked);
                 if (trav == 0u) break;
+#if BVR_LEAF_BATCH > 1
                 const unsigned blk = __ballot_sync(full, parked && cur >= LEAFV);
                 if (blk != 0u) {
+#else
+                if (__any_sync(full, parked && cur >= LEAFV)) {
+#endif
                     // (waiting for 2, 3, 4 blocked lanes before testing measured 48.4 / 48.4 / 48.6 ms against 48.5 on C2 and
                     // 376 against 371 ms on C4: this loop tests as soon as one lane is blocked, BVR_LEAF_BATCH > 1 = the knob)
 #if BVR_LEAF_BATCH > 1
