@@ -33,9 +33,6 @@ enum Kind : int { K_NONE = 0, K_MISS = 1, K_METAL = 2, K_GLASS = 3, K_DIFFUSE = 
 #ifndef BVR_FAR_GENERIC
 #define BVR_FAR_GENERIC 1      // MODE 5: far rays pick their records through a generic pointer (no predicated second load path)
 #endif
-#ifndef BVR_LDG_TOGETHER
-#define BVR_LDG_TOGETHER 1     // MODE 3: both halves of a 64-byte record in one asm statement (issued back to back)
-#endif
 #ifndef BVR_LEAF_BATCH
 #define BVR_LEAF_BATCH 1       // lean loop: parked leaves are tested once this many lanes are blocked
 #endif
@@ -590,22 +587,9 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
                                 qa = lds128u(na); qb = lds128u(na + 16u); qc = lds128u(na + 32u); qd = lds128u(na + 48u);
                             } else {
                                 const uint4* np = sv.nodes4_q + 4u * c;
-#if BVR_LDG_TOGETHER
                                 if (n_hot == 0u) ldg512u<0>(np, qa, qb, qc, qd);
                                 else if (c < n_hot) ldg512u<1>(np, qa, qb, qc, qd);
                                 else ldg512u<2>(np, qa, qb, qc, qd);
-#else
-                                if (n_hot == 0u) {
-                                    ldg256u(np, qa, qb);
-                                    ldg256u(np + 2, qc, qd);
-                                } else if (c < n_hot) {
-                                    ldg256u_keep(np, qa, qb);
-                                    ldg256u_keep(np + 2, qc, qd);
-                                } else {
-                                    ldg256u_stream(np, qa, qb);
-                                    ldg256u_stream(np + 2, qc, qd);
-                                }
-#endif
                             }
                             float e;
                             uint32_t k0 = box_cull_q16(qa.x, qa.y, qa.z, inv, noi, snx, sny, snz, sfx, sfy, sfz, closest.t, e)

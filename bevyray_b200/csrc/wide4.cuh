@@ -61,17 +61,6 @@ __device__ __forceinline__ void ldg512u(const uint4* p, uint4& a, uint4& b, uint
     else BVR_LDG512("");
 #undef BVR_LDG512
 }
-// the same load with an L1 policy: evict-last for records every ray reads (the top of the tree), no-allocate for the rest
-__device__ __forceinline__ void ldg256u_keep(const uint4* p, uint4& a, uint4& b) {
-    asm volatile("ld.global.nc.L1::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-                 : "l"(p));
-}
-__device__ __forceinline__ void ldg256u_stream(const uint4* p, uint4& a, uint4& b) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-                 : "l"(p));
-}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
