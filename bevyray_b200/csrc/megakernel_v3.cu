@@ -718,7 +718,7 @@ int launch_v3(const RenderParams& p, uint32_t n_inner, uint32_t n_models, uint32
     const bool both = tight && !no_both && both_bytes + (size_t)THREADS * cap4 * sizeof(uint32_t) <= max_smem;
     if (s4) {
         // tuned on C2 (profiles/r01_tuning_sweeps.txt): the 4-wide walk wants later shading and immediate leaf tests
-        if (tune.shade_wait_lanes == 0u) tune.shade_wait_lanes = 29u;
+        if (tune.shade_wait_lanes == 0u) tune.shade_wait_lanes = 22u;   // 20 / 22 / 24 / 26 / 29 lanes: 47.4 / 47.3 / 47.4 / 47.6 / 47.8 ms
         if (tune.leaf_batch_lanes == 0u) tune.leaf_batch_lanes = 1u;
         const size_t smem4 = (both ? both_bytes : scene4_bytes) + (size_t)THREADS * cap4 * sizeof(uint32_t);
         auto k4 = both ? megakernel_v3<THREADS, 6> : (tight ? megakernel_v3<THREADS, 5> : megakernel_v3<THREADS, 4>);
