@@ -7,6 +7,13 @@ use std::os::raw::{c_char, c_int, c_void};
 
 pub const BVR_OK: c_int = 0;
 pub const BVR_ERR_UNSUPPORTED_PROJECTION: c_int = 3;
+/// BvrRenderFlags (include/bevyray_b200.h)
+pub const BVR_RENDER_DEFER_COMPOSITE: u32 = 1;
+pub const BVR_RENDER_EXTRA_SAMPLE: u32 = 2;
+/// BVR_RENDER_EXTRA_SAMPLE_BITS: the 8x4 tiles with ((tx + ty + phase) % modulus) < count take one sample more
+pub const fn bvr_render_extra_sample_bits(modulus: u32, phase: u32, count: u32) -> u32 {
+    BVR_RENDER_EXTRA_SAMPLE | (modulus << 8) | (phase << 16) | (count << 24)
+}
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
