@@ -40,7 +40,8 @@ for env in variants:
 # scenes walked in HBM/L2: 4-wide 16-bit records, 2-wide 16-bit records, fp32 records
 big = bvr.Scene.random(7, 6000, 36.0, 0.05, 0.25)
 bref = None
-for env in ({}, {"BVR_NO_BVH4": "1"}, {"BVR_NO_Q16": "1"}):
+for env in ({}, {"BVR_NO_BVH4": "1"}, {"BVR_NO_Q16": "1"}, {"BVR_W4_LEAN": "0"}, {"BVR_W4_LEAN": "0", "BVR_TOP_RECORDS": "300"},
+            {"BVR_NO_TOP": "1"}, {"BVR_HOT_RECORDS": "40"}):
     os.environ.update(env)
     ctx.reload_tuning()
     ctx.upload_scene(big.models, big.materials, big.nodes)
@@ -57,4 +58,23 @@ ctx.upload_scene(scene.models, scene.materials, scene.nodes)
 out = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
 del os.environ["BVR_GPU_VALIDATE"]
 print("gpu-validate", all(np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)) for k in ref))
+# pixel-queue order fed back from the previous frame (tile_order.cu), uneven sample counts, weighted stores, slot sum
+os.environ["BVR_TILE_ORDER"] = "2"
+ctx.reload_tuning()
+ctx.upload_scene(scene.models, scene.materials, scene.nodes)
+for frame in range(3):
+    out = ctx.render(cam, 3, win, bvr.make_options(W, kernel=1))
+    print("tile order, frame", frame, all(np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)) for k in ref))
+del os.environ["BVR_TILE_ORDER"]
+ctx.reload_tuning()
+o = bvr.make_options(W, output_weight=0.125)
+o.flags |= bvr.capi.render_extra_sample_bits(3, 1, 2)
+out = ctx.render(cam, 3, win, o)
+print("extra sample + weight", ctx.stats()["paths"])
+import torch  # noqa: E402
+slots = torch.rand((3, 4 * 256), device="cuda")
+dst = torch.empty(4 * 256, device="cuda")
+ctx.sum_slots_device(slots.data_ptr(), 4 * 256, 3, 0b101, dst.data_ptr(), 4 * 256)
+ctx.sync()
+print("sum slots", bool(torch.equal(dst, slots[0] + slots[2])))
 print("done")
