@@ -860,6 +860,11 @@ static int build_params(BvrContext* ctx, const BvrCamera* camera, const BvrRaytr
     p.out_weight = opts->output_weight == 0.0f ? 1.0f : opts->output_weight;
     p.weight_in_kernel = 0u;
     p.extra_modulus = p.extra_phase = p.extra_count = 0u;
+    {
+        const uint32_t spp = camera->sample_count;
+        p.inv_pow2_samples = (spp != 0u && (spp & (spp - 1u)) == 0u && !(opts->flags & BVR_RENDER_EXTRA_SAMPLE))
+                                 ? 1.0f / (float)spp : 0.0f;   // exact: a power of two up to 2^31
+    }
     if (opts->flags & BVR_RENDER_EXTRA_SAMPLE) {
         p.extra_modulus = (opts->flags >> 8) & 0xffu;
         p.extra_phase = (opts->flags >> 16) & 0xffu;

@@ -36,6 +36,8 @@ struct RenderParams {
     float out_weight;                  // BvrRenderOptions.output_weight (1 = none): applied to rgba and rt_depth as they are stored
     uint32_t extra_modulus, extra_phase, extra_count;   // BVR_RENDER_EXTRA_SAMPLE (modulus 0 = off): the pixels of the 8x4 tiles
                                        // with ((tx + ty + phase) % modulus) < count take one sample more (megakernel_v3 only)
+    float inv_pow2_samples;            // 1 / sample_count when that is a power of two and every pixel takes sample_count samples
+                                       // (x * 2^-k == x / 2^k bit for bit), else 0: megakernel_v3 divides
     uint32_t weight_in_kernel;         // set by the kernel that applies out_weight itself (others get a scale pass afterwards)
 };
 

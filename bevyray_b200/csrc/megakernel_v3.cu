@@ -36,6 +36,9 @@ enum Kind : int { K_NONE = 0, K_MISS = 1, K_METAL = 2, K_GLASS = 3, K_DIFFUSE = 
 #ifndef BVR_LEAF_BATCH
 #define BVR_LEAF_BATCH 1       // lean loop: parked leaves are tested once this many lanes are blocked
 #endif
+#ifndef BVR_POW2_ALL_MODES
+#define BVR_POW2_ALL_MODES 1   // 0: only the shared-memory modes multiply by 1/n when n is a power of two
+#endif
 #ifndef BVR_RECONVERGE
 #define BVR_RECONVERGE 1
 #endif
@@ -351,8 +354,19 @@ __global__ void __launch_bounds__(THREADS) megakernel_v3(const RenderParams p, u
             const uint32_t gy = shard_global_row(p.shard, ly);
             // BVR_RENDER_EXTRA_SAMPLE: the pixels of some tiles took one sample more than cam.sample_count
             const float n = (float)(cam.sample_count + (extra_sample(p, px, gy) ? 1u : 0u));
-            float4 out = make_float4(fdiv(total.x, n), fdiv(total.y, n), fdiv(total.z, n), 1.0f);
-            const float depth_avg = fdiv(total_depth, n);
+            // total / n (raytrace.wgsl:170).  When n is a power of two, x * (1/n) IS x / n — both round the same exact value
+            // x * 2^-k once — so the four IEEE divisions (some forty instructions at one or two active lanes) become four
+            // multiplications: what a 1-spp or 4-spp frame mostly consists of is this per-pixel code.
+            float4 out;
+            float depth_avg;
+            if ((BVR_POW2_ALL_MODES || S4) && p.inv_pow2_samples != 0.0f) {
+                const float r = p.inv_pow2_samples;
+                out = make_float4(fmul(total.x, r), fmul(total.y, r), fmul(total.z, r), 1.0f);
+                depth_avg = fmul(total_depth, r);
+            } else {
+                out = make_float4(fdiv(total.x, n), fdiv(total.y, n), fdiv(total.z, n), 1.0f);
+                depth_avg = fdiv(total_depth, n);
+            }
             if (cam.level == 1u || cam.level == 2u) {
                 const size_t gpix = (size_t)gy * cam.width + px;
                 if (raster_wins(cam, p.raster_depth[gpix], depth_avg)) out = p.raster_rgba[gpix];
