@@ -1006,12 +1006,14 @@ static int render_device_impl(BvrContext* ctx, const BvrCamera* camera, const Bv
     for (uint32_t ly = 0; ly < p.shard.rows; ly++) if (shard_global_row(p.shard, ly) < p.cam.height) rows++;
     ctx->stats.paths = p.cam.level == 0u ? 0u : rows * (uint64_t)p.cam.width * p.cam.sample_count;
     if (p.extra_modulus) {   // + one path per pixel of the tiles that take an extra sample
+        // pixels of one row that sit in such a tile, by the class (ty + phase) % modulus of the row's tile row
+        std::vector<uint64_t> per_class(p.extra_modulus, 0);
+        for (uint32_t r = 0; r < p.extra_modulus; r++)
+            for (uint32_t tx = 0; tx * 8u < p.cam.width; tx++)
+                if ((tx + r) % p.extra_modulus < p.extra_count) per_class[r] += std::min(8u, p.cam.width - tx * 8u);
         for (uint32_t ly = 0; ly < p.shard.rows; ly++) {
             const uint32_t gy = shard_global_row(p.shard, ly);
-            if (gy >= p.cam.height) continue;
-            for (uint32_t tx = 0; tx * 8u < p.cam.width; tx++)
-                if ((tx + (gy >> 2) + p.extra_phase) % p.extra_modulus < p.extra_count)
-                    ctx->stats.paths += std::min(8u, p.cam.width - tx * 8u);
+            if (gy < p.cam.height) ctx->stats.paths += per_class[((gy >> 2) + p.extra_phase) % p.extra_modulus];
         }
     }
     return BVR_OK;
