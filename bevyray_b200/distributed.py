@@ -179,12 +179,12 @@ class ShardedRenderer:
         """Makes sure the slot buffer for frames of this size exists on rank 0 and is mapped on every rank.  Collective.
         Returns False (on every rank) when peer memory is not available: the caller then uses the NCCL reduce."""
         key = (rows, width)
+        if self._slots is False:                # peer memory was refused once: stay with the NCCL reduce
+            return False
         if self._slots is not None:
             if self._slots[0] == key:
                 return True
             self._release_slots()
-        if self._slots is False:
-            return False
         floats = rows * width * 4
         ok, ptr = 1, 0
         handle = torch.zeros(capi.PEER_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
@@ -232,8 +232,9 @@ class ShardedRenderer:
         if cam.sample_count > 0:
             self.ctx.render_device(cam, lv, win, opts, 0, 0, rgba=half + self.rank * floats * 4)   # (may refuse: see caller)
         self._slot_phase = phase ^ 1
-        done = self._buf("done", (1,), torch.float32)
-        dist.all_reduce(done)                   # every rank's render kernel — and with it its pixel stores — is complete
+        if ("done", (1,), torch.float32) not in self._bufs:
+            self._buf("done", (1,), torch.float32).zero_()
+        dist.all_reduce(self._buf("done", (1,), torch.float32))   # every rank's render kernel — and with it its pixel stores — is complete
         if self.rank != 0:
             return local
         full = self._buf("full_samples", (rows, width, 4), torch.float32)
