@@ -1,6 +1,6 @@
 #!/bin/bash
 # two-GPU tests of the sharded renderer + a two-rank bench run (gpurun --gpus 2 -- bash tools/run_multi_2gpu.sh)
-cd $GRAFT_REPO_ROOT
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" && mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/multi2_gpus.txt
 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -rs > gpurun_out/multi2_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/multi2_pytest.log
